@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CARMA(p,q) Kalman log-likelihood hot path on B200.
+
+Metric (BASELINE.json): CARMA(5,3) ny=270 log-likelihood evals/s.  One "step" = one pass of the hot
+path over one batch of synthetic input = 65,536 LogDensity evaluations per GPU on one ny=270 light
+curve (BASELINE config 2).  With N GPUs every rank evaluates its own 65,536-row batch (weak
+scaling, no data-path collective).  The PT-MCMC secondary metric (ensemble-iterations/s, BASELINE
+config 3) is measured in the same run and reported under "pt_mcmc".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P, Q, NY, NTHETA = 5, 3, 270, 65536
+METRIC = "CARMA(5,3) ny=270 loglik evals/s"
+UNIT = "evals/s"
+
+
+def f_step(p):
+    """Algorithmic FP64 flops per Kalman step: 20p^2 + 36p + 7, transcendentals excluded."""
+    return 20 * p * p + 36 * p + 7
+
+
+def f_eval(p, ny):
+    f_reset = (2.0 / 3.0) * 8 * p ** 3 + 14 * p * p + 8 * p * p
+    return (ny - 1) * f_step(p) + f_reset
+
+
+def make_inputs(seed_offset=0):
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(NY, 270)
+    th = synth.theta_batch(NTHETA, t, y, p=P, q=Q, seed=1000 + seed_offset)
+    return t, y, e, th
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(float(f[0]))
+                    self.sm_max = float(f[1])
+                    for nm, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def _oracle_worker(args):
+    from oracle import oracle as O
+    t, y, e, th = args
+    pr = O.default_prior(t, y)
+    return O.logdensity(O.KIND_CARMA, P, Q, t, y, e, th, prior=pr, fast=True)
+
+
+def cpu_oracle_rate(t, y, e, th, cores):
+    """evals/s of the CPU oracle (oracle/carma_oracle.cpp, -O3 x86-64-v3) on `cores` processes."""
+    from oracle import oracle as O
+    O.build()
+    if cores == 1:
+        t0 = time.perf_counter()
+        _oracle_worker((t, y, e, th))
+        return th.shape[0] / (time.perf_counter() - t0)
+    import multiprocessing as mp
+    chunks = np.array_split(th, cores)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_worker, [(t, y, e, c[:64]) for c in chunks])  # warm the pool
+        t0 = time.perf_counter()
+        pool.map(_oracle_worker, [(t, y, e, c) for c in chunks])
+        dt = time.perf_counter() - t0
+    return th.shape[0] / dt
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU algorithm for this path (oracle port; the reference itself
+    needs Armadillo+Boost and cannot be built here) on all host cores, same config/metric/unit."""
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    t, y, e, th = make_inputs()
+    sample = th[:16384] if cores < 16 else th
+    if args.warmup > 0:
+        cpu_oracle_rate(t, y, e, sample[:2048], cores)
+    t0 = time.perf_counter()
+    rates = [cpu_oracle_rate(t, y, e, sample, cores) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched log-likelihood: CARMA(5,3) parameter vectors on one ny=270 series "
+                               "(BASELINE config 2)", "p": P, "q": Q, "ny": NY, "thetas_per_step": int(sample.shape[0])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of the 65,536 theta rows per step, split over %d processes" % (sample.shape[0], cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import carma_pack_b200 as C
+    import ctypes
+
+    if not torch.cuda.is_available() or C._lib.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    t, y, e, th = make_inputs(seed_offset=rank)
+    series = C.Series(t, y, e, device=dev)
+    prior = series.default_prior()
+    d = th.shape[1]
+    d_theta = torch.from_numpy(th).to("cuda", non_blocking=False)
+    d_out = torch.empty(NTHETA, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        series.loglik_dev(C.KIND_CARMA, P, Q, d_theta.data_ptr(), d_out.data_ptr(), NTHETA, prior, 0, stream)
+
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    fp64_peak = C._lib.fp64_peak_tflops(dev)  # measured DFMA saturation on this GPU, before the timed region
+
+    sampler = ClockSampler(dev) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.zero_()  # L2 flush between timed iterations, outside the per-step event pair
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    if dist:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H per step)
+    h_theta = torch.from_numpy(th).pin_memory()
+    h_out = torch.empty(NTHETA, dtype=torch.float64).pin_memory()
+    lib = C._lib.lib
+
+    def e2e_step():
+        C._lib.check(lib.carma_loglik_batch(series.handle, C.KIND_CARMA, P, Q, ctypes.byref(prior), NTHETA,
+                                            h_theta.data_ptr(), h_out.data_ptr(), 0), "carma_loglik_batch")
+
+    for _ in range(3):
+        e2e_step()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()  # synchronous: returns after the D2H copy completed
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    checksum = float(np.nansum(np.where(np.isfinite(h_out.numpy()), h_out.numpy(), 0.0)))
+    same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy(), equal_nan=True))
+
+    # ---- PT-MCMC secondary metric (BASELINE config 3 shape: 10 temperatures, ny=1000, on-device adapt/exchange)
+    pt = None
+    if not args.no_pt:
+        from carma_pack_b200 import synth
+        n_ens = args.pt_ensembles
+        tp, yp, ep = synth.readme_series(1000, 1000)
+        sp = C.Series(tp, yp, ep, device=dev)
+        ppr = sp.default_prior()
+        o = C.PTOpts()
+        lib.carma_pt_default_opts(ctypes.byref(o))
+        o.nsamples, o.burnin, o.thin, o.ntemps = args.pt_iters // 2, args.pt_iters - args.pt_iters // 2, 1, 10
+        o.seed, o.ensemble_offset = 4096, rank * n_ens
+        iters = o.burnin + o.nsamples
+        ds = torch.empty(n_ens * o.nsamples * d, dtype=torch.float64, device="cuda")
+        dl = torch.empty(n_ens * o.nsamples, dtype=torch.float64, device="cuda")
+        o_w = C.PTOpts.from_buffer_copy(o)
+        o_w.nsamples, o_w.burnin = 1, 1
+        sp.pt_run_dev(C.KIND_CARMA, P, Q, o_w, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)  # warm-up
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sp.pt_run_dev(C.KIND_CARMA, P, Q, o, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        pt_ms = a.elapsed_time(b)
+        if dist:
+            tt = torch.tensor([pt_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            pt_ms = float(tt.item())
+        # the launch also draws starting values: (iters + ~1 start eval) evals per chain
+        pt = {"metric": "PT-MCMC ensemble-iterations/s, CARMA(5,3), ny=1000, 10 temperatures, order=reference(pipelined)",
+              "value": world * n_ens * iters / (pt_ms * 1e-3), "unit": "ensemble-iters/s",
+              "implied_evals_per_s": world * n_ens * iters * 10 / (pt_ms * 1e-3),
+              "ensembles_per_gpu": n_ens, "iterations": iters, "ms": pt_ms, "kernel_launches": 1,
+              "tflops_algorithmic": world * n_ens * iters * 10 * f_eval(P, 1000) / (pt_ms * 1e-3) / 1e12,
+              "finite_logposts": bool(torch.isfinite(dl).all().item())}
+        sp.close()
+
+    # ---- NCCL: gather per-rank summaries only (no data-path collective)
+    summary = [float(torch.nan_to_num(d_out, neginf=-1e300).max().item()), float(torch.isfinite(d_out).sum().item())]
+    if dist:
+        g = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(g, torch.tensor(summary, dtype=torch.float64, device="cuda"))
+        summary = [max(float(x[0]) for x in g), sum(float(x[1]) for x in g)]
+
+    if rank == 0:
+        evals = world * NTHETA * K
+        value = evals / (total_ms * 1e-3)
+        kern_ms = float(np.mean(step_ms))
+        fe = f_eval(P, NY)
+        achieved_tf = NTHETA * fe / (kern_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = NTHETA * (8 * d + 8) + 24 * NY
+        # CPU baseline beside it: oracle port, one core, the same 65,536-row batch (about 5-8 s)
+        cpu = None
+        if not args.no_cpu:
+            rate1 = cpu_oracle_rate(t, y, e, th, 1)
+            cpu = {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "the full 65,536-row theta batch of one step, once, one core, oracle -O3 x86-64-v3"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batched log-likelihood: 65,536 CARMA(5,3) parameter vectors on one ny=270 "
+                                   "series per GPU (BASELINE config 2)", "p": P, "q": Q, "ny": NY,
+                       "thetas_per_gpu": NTHETA, "l2": "256 MB buffer written between timed steps (outside the event pairs)",
+                       "timing": "CUDA events on the launching stream, per step; sum over K steps; max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": world * NTHETA * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": NTHETA * d * 8,
+                    "d2h_bytes_per_step": NTHETA * 8, "api": "carma_loglik_batch (host buffers, pinned)",
+                    "matches_device_path": same},
+            "gpu_launches": K,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "loglik_batch_kernel<5>", "kernel_ms": kern_ms,
+                         "flops_per_eval": fe, "flops_per_step_formula": "20p^2+36p+7 (SURVEY 8d), transcendentals excluded",
+                         "peak_source": "DFMA saturation micro-benchmark run on this GPU in this process "
+                                        "(carma_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "algorithmic_bytes_per_launch": alg_bytes,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
+            "cpu_baseline": cpu,
+            "pt_mcmc": pt,
+            "summary": {"max_logpost": summary[0], "finite_rows": summary[1], "checksum_rank0": checksum},
+        }
+        print(json.dumps(line))
+    series.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-pt", action="store_true", help="skip the PT-MCMC secondary measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU baseline")
+    ap.add_argument("--pt-ensembles", type=int, default=4096)
+    ap.add_argument("--pt-iters", type=int, default=20)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,320 @@
+"""ctypes binding of the C ABI in include/carma_b200.h (libcarma_b200.so).
+
+This is the only way Python reaches the GPU path.  There is no CPU fallback: if the shared
+library is missing the import fails loudly, and every compute call raises CarmaError when CUDA is
+unavailable.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcarma_b200.so")
+
+KIND_CAR1, KIND_CARP, KIND_CARMA, KIND_ZCAR, KIND_ZCARMA = 0, 1, 2, 3, 4
+IGNORE_BOUNDS, LOGLIK_ONLY = 1, 2
+MAX_P = 7
+
+EXPORTED_SYMBOLS = [
+    "carma_last_error", "carma_abi_version", "carma_device_count",
+    "carma_series_create", "carma_series_destroy", "carma_series_length", "carma_series_default_prior",
+    "carma_loglik_batch_dev", "carma_loglik_batch", "carma_log_prior",
+    "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
+    "carma_multi_loglik_dev", "carma_multi_loglik",
+    "carma_filter", "carma_predict",
+    "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev",
+    "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev",
+]
+
+
+class CarmaError(RuntimeError):
+    pass
+
+
+class Prior(ctypes.Structure):
+    _fields_ = [("max_stdev", ctypes.c_double), ("max_freq", ctypes.c_double), ("min_freq", ctypes.c_double),
+                ("kappa_low", ctypes.c_double), ("kappa_high", ctypes.c_double), ("measerr_dof", ctypes.c_double)]
+
+    def as_tuple(self):
+        return (self.max_stdev, self.max_freq, self.min_freq, self.kappa_low, self.kappa_high, self.measerr_dof)
+
+
+PRIOR_DTYPE = np.dtype([("max_stdev", "f8"), ("max_freq", "f8"), ("min_freq", "f8"), ("kappa_low", "f8"),
+                        ("kappa_high", "f8"), ("measerr_dof", "f8")])
+
+
+class PTOpts(ctypes.Structure):
+    _fields_ = [("nsamples", ctypes.c_int), ("burnin", ctypes.c_int), ("thin", ctypes.c_int),
+                ("ntemps", ctypes.c_int), ("tmax", ctypes.c_double), ("dof", ctypes.c_int),
+                ("target_rate", ctypes.c_double), ("gamma", ctypes.c_double), ("seed", ctypes.c_uint64),
+                ("ensemble_offset", ctypes.c_uint32), ("max_start_attempts", ctypes.c_int),
+                ("order_mode", ctypes.c_int), ("record_trace", ctypes.c_int)]
+
+
+TRACE_DTYPE = np.dtype([("lp_prop", "f8"), ("lp_cur", "f8"), ("alpha", "f8"), ("u", "f8"),
+                        ("accepted", "i4"), ("pad", "i4")])
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "carma_pack_b200: %s is missing. Build it with `python -m carma_pack_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.carma_last_error.restype = ctypes.c_char_p
+    pr = ctypes.POINTER(Prior)
+    L.carma_series_create.argtypes = [_dp, _dp, _dp, _sz, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.carma_series_destroy.argtypes = [_vp]
+    L.carma_series_length.argtypes = [_vp, ctypes.POINTER(_sz)]
+    L.carma_series_default_prior.argtypes = [_vp, ctypes.c_int, pr]
+    L.carma_loglik_batch_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp,
+                                         ctypes.c_uint, _vp]
+    L.carma_loglik_batch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp, ctypes.c_uint]
+    L.carma_log_prior.argtypes = [ctypes.c_int, ctypes.c_int, _dp, pr, _dp]
+    L.carma_multi_series_create.argtypes = [_dp, _dp, _dp, ctypes.POINTER(ctypes.c_int64), _sz, ctypes.c_int,
+                                            ctypes.POINTER(_vp)]
+    L.carma_multi_series_destroy.argtypes = [_vp]
+    L.carma_multi_series_default_priors.argtypes = [_vp, ctypes.c_int, _vp]
+    L.carma_multi_loglik_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
+                                         ctypes.c_uint, _vp]
+    L.carma_multi_loglik.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_uint]
+    L.carma_filter.argtypes = [_vp, ctypes.c_double, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, _dp]
+    L.carma_predict.argtypes = [_vp, ctypes.c_double, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                _dp, _sz, _dp, _dp]
+    L.carma_pt_default_opts.argtypes = [ctypes.POINTER(PTOpts)]
+    L.carma_pt_default_opts.restype = None
+    L.carma_pt_run.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.POINTER(PTOpts), _sz,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.carma_pt_run_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.POINTER(PTOpts), _sz,
+                                   _vp, _vp, _vp, _vp, _vp, _vp]
+    L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
+    L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
+    L.carma_tdist_dev.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _dp]
+    return L
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib.carma_last_error()
+        raise CarmaError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def model_dim(kind, p, q):
+    if kind == KIND_CAR1:
+        return 4
+    if kind == KIND_CARMA:
+        return 3 + p + q
+    if kind == KIND_ZCARMA:
+        return 4 + p
+    return 3 + p
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    rc = lib.carma_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class Series:
+    """One light curve resident in HBM (carma_series_t)."""
+
+    def __init__(self, time, y, yerr, device=0):
+        t, yy, ee = _c(time), _c(y), _c(yerr)
+        if not (t.shape == yy.shape == ee.shape and t.ndim == 1):
+            raise ValueError("time, y, yerr must be 1-d arrays of equal length")
+        self.handle = _vp()
+        check(lib.carma_series_create(_ptr(t), _ptr(yy), _ptr(ee), t.size, device, ctypes.byref(self.handle)),
+              "carma_series_create")
+        self.ny = t.size
+        self.device = device
+        self.time, self.y, self.yerr = t, yy, ee
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.carma_series_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def default_prior(self, population_var=True):
+        pr = Prior()
+        check(lib.carma_series_default_prior(self.handle, int(population_var), ctypes.byref(pr)), "default_prior")
+        return pr
+
+    def loglik(self, kind, p, q, theta, prior=None, flags=0):
+        """Batched CARMA_Base::LogDensity with host arrays (H2D + kernel + D2H inside)."""
+        th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        d = model_dim(kind, p, q)
+        if th.shape[1] != d:
+            raise ValueError("theta must have %d columns for this model, got %d" % (d, th.shape[1]))
+        if prior is None:
+            prior = self.default_prior()
+        out = np.empty(th.shape[0])
+        check(lib.carma_loglik_batch(self.handle, kind, p, q, ctypes.byref(prior), th.shape[0],
+                                     th.ctypes.data, out.ctypes.data, flags), "carma_loglik_batch")
+        return out
+
+    def loglik_dev(self, kind, p, q, d_theta_ptr, d_out_ptr, n, prior, flags=0, stream=0):
+        """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr()), no sync."""
+        check(lib.carma_loglik_batch_dev(self.handle, kind, p, q, ctypes.byref(prior), n, d_theta_ptr, d_out_ptr,
+                                         flags, stream), "carma_loglik_batch_dev")
+
+    def filter(self, sigsqr, omega, ma, measerr_scale=1.0, mu=0.0):
+        om = np.asarray(omega, dtype=complex).ravel()
+        p = om.size
+        buf = np.empty(2 * p)
+        buf[0::2], buf[1::2] = om.real, om.imag
+        m = np.zeros(p)
+        m[:len(ma)] = ma
+        mean, var = np.empty(self.ny), np.empty(self.ny)
+        check(lib.carma_filter(self.handle, sigsqr, _ptr(buf), _ptr(m), p, measerr_scale, mu, _ptr(mean), _ptr(var)),
+              "carma_filter")
+        return mean, var
+
+    def predict(self, sigsqr, omega, ma, tq, measerr_scale=1.0, mu=0.0):
+        om = np.asarray(omega, dtype=complex).ravel()
+        p = om.size
+        buf = np.empty(2 * p)
+        buf[0::2], buf[1::2] = om.real, om.imag
+        m = np.zeros(p)
+        m[:len(ma)] = ma
+        q = _c(np.atleast_1d(tq))
+        qm, qv = np.empty(q.size), np.empty(q.size)
+        check(lib.carma_predict(self.handle, sigsqr, _ptr(buf), _ptr(m), p, measerr_scale, mu, _ptr(q), q.size,
+                                _ptr(qm), _ptr(qv)), "carma_predict")
+        return qm, qv
+
+    def pt_run(self, kind, p, q, nsamples, burnin, thin=1, ntemps=10, n_ensembles=1, seed=1, ensemble_offset=0,
+               init=None, prior=None, order_mode=0, record_trace=False, tmax=100.0, dof=8, target_rate=0.25,
+               gamma=2.0 / 3.0, max_start_attempts=1000):
+        """RunCarmaSampler for n_ensembles independent ensembles, fully on device."""
+        d = model_dim(kind, p, q)
+        if prior is None:
+            prior = self.default_prior()
+        o = PTOpts()
+        lib.carma_pt_default_opts(ctypes.byref(o))
+        o.nsamples, o.burnin, o.thin, o.ntemps = int(nsamples), int(burnin), int(thin), int(ntemps)
+        o.tmax, o.dof, o.target_rate, o.gamma = tmax, dof, target_rate, gamma
+        o.seed, o.ensemble_offset, o.max_start_attempts = seed, ensemble_offset, max_start_attempts
+        o.order_mode, o.record_trace = order_mode, int(record_trace)
+        samples = np.empty((n_ensembles, nsamples, d))
+        logposts = np.empty((n_ensembles, nsamples))
+        acc = np.empty((n_ensembles, ntemps))
+        xr = np.empty((n_ensembles, ntemps))
+        iters = burnin + nsamples * thin
+        rt = xt = prop = None
+        if record_trace:
+            rt = np.zeros((n_ensembles, iters, ntemps), dtype=TRACE_DTYPE)
+            xt = np.zeros((n_ensembles, iters, ntemps), dtype=TRACE_DTYPE)
+            prop = np.zeros((n_ensembles, iters, ntemps, d))
+        initp = None
+        if init is not None and len(init) == d:
+            init = _c(init)
+            initp = init.ctypes.data
+        check(lib.carma_pt_run(self.handle, kind, p, q, ctypes.byref(prior), ctypes.byref(o), n_ensembles, initp,
+                               samples.ctypes.data, logposts.ctypes.data, acc.ctypes.data, xr.ctypes.data,
+                               rt.ctypes.data if record_trace else None, xt.ctypes.data if record_trace else None,
+                               prop.ctypes.data if record_trace else None), "carma_pt_run")
+        res = dict(samples=samples, logposts=logposts, accept_rates=acc, exchange_rates=xr)
+        if record_trace:
+            res.update(ram_trace=rt, exchange_trace=xt, proposals=prop)
+        return res
+
+    def pt_run_dev(self, kind, p, q, opts, n_ensembles, d_samples, d_logposts, prior, d_init=None, d_accept=None,
+                   d_exchange=None, stream=0):
+        check(lib.carma_pt_run_dev(self.handle, kind, p, q, ctypes.byref(prior), ctypes.byref(opts), n_ensembles,
+                                   d_init, d_samples, d_logposts, d_accept, d_exchange, stream), "carma_pt_run_dev")
+
+
+class MultiSeries:
+    """Ragged batch of light curves (CSR offsets) resident in HBM (carma_multi_series_t)."""
+
+    def __init__(self, time, y, yerr, offsets, device=0):
+        t, yy, ee = _c(time), _c(y), _c(yerr)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.ncurves = off.size - 1
+        self.handle = _vp()
+        check(lib.carma_multi_series_create(_ptr(t), _ptr(yy), _ptr(ee),
+                                            off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), self.ncurves, device,
+                                            ctypes.byref(self.handle)), "carma_multi_series_create")
+        self.offsets = off
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.carma_multi_series_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def default_priors(self, population_var=True):
+        out = np.empty(self.ncurves, dtype=PRIOR_DTYPE)
+        check(lib.carma_multi_series_default_priors(self.handle, int(population_var), out.ctypes.data), "default_priors")
+        return out
+
+    def loglik(self, kind, p, q, theta, priors=None, flags=0):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        d = model_dim(kind, p, q)
+        if th.shape != (self.ncurves, d):
+            raise ValueError("theta must be (%d, %d)" % (self.ncurves, d))
+        out = np.empty(self.ncurves)
+        pp = None
+        if priors is not None:
+            priors = np.ascontiguousarray(priors, dtype=PRIOR_DTYPE)
+            pp = priors.ctypes.data
+        check(lib.carma_multi_loglik(self.handle, kind, p, q, pp, th.ctypes.data, out.ctypes.data, flags),
+              "carma_multi_loglik")
+        return out
+
+    def loglik_dev(self, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags=0, stream=0):
+        check(lib.carma_multi_loglik_dev(self.handle, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags, stream),
+              "carma_multi_loglik_dev")
+
+
+def log_prior(kind, p, theta, prior):
+    th = _c(theta)
+    out = ctypes.c_double()
+    check(lib.carma_log_prior(kind, p, _ptr(th), ctypes.byref(prior), ctypes.byref(out)), "carma_log_prior")
+    return out.value
+
+
+def fp64_peak_tflops(device=0):
+    out = ctypes.c_double()
+    check(lib.carma_fp64_peak_tflops(device, ctypes.byref(out)), "carma_fp64_peak_tflops")
+    return out.value
+
+
+def philox_dev(c0, c1, c2, c3, seed):
+    out = (ctypes.c_uint32 * 4)()
+    check(lib.carma_philox_dev(c0, c1, c2, c3, seed, out), "carma_philox_dev")
+    return [int(x) for x in out]
+
+
+def tdist_dev(seed, chain, it, j, dof=8):
+    out = ctypes.c_double()
+    check(lib.carma_tdist_dev(seed, chain, it, j, dof, ctypes.byref(out)), "carma_tdist_dev")
+    return out.value

@@ -1,0 +1,686 @@
+// loglik.cu -- batched CARMA log-density kernels (K1/K2/K4) and the explicit-parameter
+// filter / predict kernels, plus their C-ABI entry points.
+//
+// K1  loglik_batch_kernel<P>:  one thread = one theta = one complete LogDensity
+//     (carpack.hpp:131-176 -> kfilter.cpp:138-215).  The light curve (dt, y, yerr^2) is staged once
+//     per block in shared memory by the TMA engine (cp.async.bulk + mbarrier, double buffered for
+//     long series) and read by every thread with broadcast LDS; the filter state lives in registers.
+// K4  multi_loglik_kernel<P>:  one thread = one light curve with its own theta.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <limits>
+
+#include "kalman_real.cuh"
+#include "series.h"
+
+namespace carma {
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_BLOCK = 64;
+
+// resident blocks per SM wanted for each P (bounds the register allocation so that the
+// BASELINE batch of 65,536 thetas fits in one wave of 148 SMs: 7 x 64 x 148 = 66,304 at P = 5)
+__host__ __device__ constexpr int k1_min_blocks(int P) { return P <= 4 ? 8 : (P == 5 ? 7 : (P == 6 ? 5 : 4)); }
+
+template <int P>
+__global__ void __launch_bounds__(K1_BLOCK, k1_min_blocks(P))
+loglik_batch_kernel(SeriesView sv, int kind, int q, int d, unsigned flags, carma_prior_t prior,
+                    const double* __restrict__ theta, double* __restrict__ out, size_t n, int chunk) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+
+    const int tid = threadIdx.x;
+    const size_t row = (size_t)blockIdx.x * K1_BLOCK + tid;
+    const int ny = sv.ny;
+    const int nchunks = (ny + chunk - 1) / chunk;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        // chunk k -> buffer k&1 : three bulk copies (dt, y, e2n), byte counts multiples of 16
+        int start = k * chunk;
+        int len = min(chunk, sv.nyp - start);
+        uint32_t bytes = (uint32_t)len * 8u;
+        double* dst = smem + (size_t)(k & 1) * 3 * chunk;
+        mbar_expect_tx(&bars[k & 1], 3u * bytes);
+        bulk_g2s(dst, sv.dt + start, bytes, &bars[k & 1]);
+        bulk_g2s(dst + chunk, sv.y + start, bytes, &bars[k & 1]);
+        bulk_g2s(dst + 2 * chunk, sv.e2n + start, bytes, &bars[k & 1]);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (nbuf > 1) issue(1);
+    }
+
+    // ---- per-theta prologue (overlaps the copy)
+    RealParams<P> prm;
+    KalmanReal<P> kf;
+    LogLikAcc acc;
+    bool active = row < n;
+    int status = TT_OK;
+    if (active) {
+        double th[MAX_D];
+#pragma unroll
+        for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[row * (size_t)d + j] : 0.0;
+        status = transform_theta<P>(kind, q, flags, prior, th, prm);
+        if (status != TT_OK) active = false;
+    }
+    if (active) {
+        kf.reset(prm, sv.e2_0);
+        acc.init();
+    }
+
+    // ---- time loop
+    for (int k = 0; k < nchunks; k++) {
+        const int buf = k & 1;
+        mbar_wait(&bars[buf], (uint32_t)((k >> 1) & 1));
+        if (active) {
+            const double* sdt = smem + (size_t)buf * 3 * chunk;
+            const double* sy = sdt + chunk;
+            const double* se = sdt + 2 * chunk;
+            const int start = k * chunk;
+            const int len = min(chunk, ny - start);
+            const int nadv = (start + len == ny) ? len - 1 : len;  // no advance after the last point
+            filter_span<P>(kf, acc, prm, sdt, sy, se, len, nadv);
+        }
+        if (k + 2 < nchunks) {
+            __syncthreads();  // every thread is done with this buffer
+            if (tid == 0) issue(k + 2);
+        }
+    }
+
+    if (row < n) {
+        double r;
+        if (status != TT_OK) r = -INFINITY;
+        else r = acc.value() + prm.logprior;
+        out[row] = r;
+    }
+}
+
+template <int P>
+static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsigned flags, const carma_prior_t& prior,
+                             const double* d_theta, double* d_out, size_t n, cudaStream_t stream) {
+    int chunk = std::min(sv.nyp, 512);
+    int nchunks = (sv.ny + chunk - 1) / chunk;
+    size_t smem = (size_t)(nchunks > 1 ? 2 : 1) * 3 * chunk * sizeof(double);
+    unsigned grid = (unsigned)((n + K1_BLOCK - 1) / K1_BLOCK);
+    loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n, chunk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_loglik_batch(const SeriesView& sv, int kind, int p, int q, unsigned flags,
+                                const carma_prior_t& prior, const double* d_theta, double* d_out, size_t n,
+                                cudaStream_t stream) {
+    int d = model_dim(kind, p, q);
+    switch (p) {
+        case 1: return launch_k1<1>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 2: return launch_k1<2>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 3: return launch_k1<3>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 4: return launch_k1<4>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 5: return launch_k1<5>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 6: return launch_k1<6>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        case 7: return launch_k1<7>(sv, kind, q, d, flags, prior, d_theta, d_out, n, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: one light curve per thread (ragged, CSR offsets); per-curve theta and prior
+// ---------------------------------------------------------------------------------------------
+constexpr int K4_BLOCK = 64;
+
+template <int P>
+__global__ void __launch_bounds__(K4_BLOCK)
+multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y, const double* __restrict__ e2,
+                    const long long* __restrict__ off, size_t ncurves, int kind, int q, int d, unsigned flags,
+                    const carma_prior_t* __restrict__ priors, const double* __restrict__ theta,
+                    double* __restrict__ out) {
+    const size_t c = (size_t)blockIdx.x * K4_BLOCK + threadIdx.x;
+    if (c >= ncurves) return;
+    const long long o0 = off[c], o1 = off[c + 1];
+    const int ny = (int)(o1 - o0);
+    double th[MAX_D];
+#pragma unroll
+    for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[c * (size_t)d + j] : 0.0;
+    RealParams<P> prm;
+    carma_prior_t pr = priors[c];
+    int status = transform_theta<P>(kind, q, flags, pr, th, prm);
+    if (status != TT_OK || ny <= 0) {
+        out[c] = (ny <= 0) ? 0.0 : -INFINITY;
+        return;
+    }
+    KalmanReal<P> kf;
+    LogLikAcc acc;
+    kf.reset(prm, e2[o0]);
+    acc.init();
+    const double* pdt = dt + o0;
+    const double* py = y + o0;
+    const double* pe = e2 + o0;
+    for (int i = 0; i < ny - 1; i++) {
+        double innov = (py[i] - prm.mu) - kf.mean;
+        double inv = 1.0 / kf.var;
+        acc.add(kf.var, innov, inv);
+        kf.advance(prm, innov, inv, pdt[i], pe[i + 1]);
+    }
+    {
+        double innov = (py[ny - 1] - prm.mu) - kf.mean;
+        double inv = 1.0 / kf.var;
+        acc.add(kf.var, innov, inv);
+    }
+    out[c] = acc.value() + prm.logprior;
+}
+
+cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, int q, unsigned flags,
+                                const carma_prior_t* d_priors, const double* d_theta, double* d_out,
+                                cudaStream_t stream) {
+    int d = model_dim(kind, p, q);
+    unsigned grid = (unsigned)((m->ncurves + K4_BLOCK - 1) / K4_BLOCK);
+#define LAUNCH_K4(PP)                                                                                             \
+    multi_loglik_kernel<PP><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, kind, q, \
+                                                           d, flags, d_priors, d_theta, d_out)
+    switch (p) {
+        case 1: LAUNCH_K4(1); break;
+        case 2: LAUNCH_K4(2); break;
+        case 3: LAUNCH_K4(3); break;
+        case 4: LAUNCH_K4(4); break;
+        case 5: LAUNCH_K4(5); break;
+        case 6: LAUNCH_K4(6); break;
+        case 7: LAUNCH_K4(7); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef LAUNCH_K4
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// explicit-parameter filter / predict (KalmanFilterp class API)
+// ---------------------------------------------------------------------------------------------
+struct FilterArgs {
+    double sigsqr, scale, mu;
+    double omega[2 * MAX_P];
+    double ma[MAX_P];
+    int p;
+};
+
+__global__ void filter_kernel(SeriesView sv, FilterArgs a, double* __restrict__ mean, double* __restrict__ var,
+                              int* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    KalmanCplx kf;
+    kf.scale = a.scale;
+    kf.mu = a.mu;
+    if (!kf.reset(a.sigsqr, a.omega, a.ma, a.p, sv.e2_0, sv.y[0])) {
+        *status = 1;
+        return;
+    }
+    *status = 0;
+    mean[0] = kf.mean;
+    var[0] = kf.var;
+    for (int i = 1; i < sv.ny; i++) {
+        kf.update(sv.dt[i - 1], sv.y[i], sv.e2n[i - 1]);
+        mean[i] = kf.mean;
+        var[i] = kf.var;
+    }
+}
+
+// one thread per query time (kfilter.cpp:218-286)
+__global__ void predict_kernel(SeriesView sv, FilterArgs a, const double* __restrict__ tq, size_t nq,
+                               double* __restrict__ qmean, double* __restrict__ qvar, int* __restrict__ status) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nq) return;
+    const double time = tq[k];
+    const int ny = sv.ny;
+    int ipredict = 0;
+    while (time > sv.t[ipredict]) {
+        ipredict++;
+        if (ipredict == ny) break;
+    }
+    KalmanCplx kf;
+    kf.scale = a.scale;
+    kf.mu = a.mu;
+    if (!kf.reset(a.sigsqr, a.omega, a.ma, a.p, sv.e2_0, sv.y[0])) {
+        *status = 1;
+        qmean[k] = NAN;
+        qvar[k] = NAN;
+        return;
+    }
+    for (int i = 1; i < ipredict; i++) kf.update(sv.dt[i - 1], sv.y[i], sv.e2n[i - 1]);
+    double pmean, pvar;
+    if (ipredict == 0) {
+        pmean = 0.0;
+        pvar = kf.var - a.scale * sv.e2_0;  // Re(b V b^H): kf.g still holds V b^H
+    } else {
+        kf.gain_and_advance(kf.var, fabs(time - sv.t[ipredict - 1]));
+        double m = 0.0;
+        for (int i = 0; i < kf.p; i++) m += kf.b[i].re * kf.x[i].re - kf.b[i].im * kf.x[i].im;
+        pmean = m;
+        pvar = kf.quad_form();
+    }
+    if (ipredict == ny) {
+        qmean[k] = pmean;
+        qvar[k] = pvar;
+        return;
+    }
+    double prec = 1.0 / pvar;
+    pmean *= prec;
+    auto e2_at = [&](int i) { return i == 0 ? sv.e2_0 : sv.e2n[i - 1]; };
+    kf.initialize_coefs(fabs(sv.t[ipredict] - time), pmean / prec, pvar, e2_at(ipredict));
+    prec += kf.yslope * kf.yslope / kf.var;
+    pmean += kf.yslope * ((sv.y[ipredict] - a.mu) - kf.yconst) / kf.var;
+    for (int i = ipredict + 1; i < ny; i++) {
+        kf.update_coefs(sv.dt[i - 1], sv.y[i - 1], e2_at(i));
+        prec += kf.yslope * kf.yslope / kf.var;
+        pmean += kf.yslope * ((sv.y[i] - a.mu) - kf.yconst) / kf.var;
+    }
+    pvar = 1.0 / prec;
+    pmean *= pvar;
+    qmean[k] = pmean;
+    qvar[k] = pvar;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 FMA saturation micro-benchmark (roofline denominator measured on the same GPU)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) out[0] = s;
+}
+
+__global__ void philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out) {
+    philox4x32_10(c0, c1, c2, c3, seed, out);
+}
+__global__ void tdist_kernel(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, int dof, double* out) {
+    *out = tdist_draw(seed, chain, STREAM_PROPOSAL, iter, j, dof);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+bool DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(scratch)")) return false;
+    cap = bytes;
+    return true;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+SeriesStats compute_stats(const double* t, const double* y, size_t n) {
+    SeriesStats s{};
+    double sum = 0, sq = 0;
+    for (size_t i = 0; i < n; i++) { sum += y[i]; sq += y[i] * y[i]; }
+    s.mean = sum / (double)n;
+    s.var_pop = sq / (double)n - s.mean * s.mean;  // carmcmc.cpp:85-88
+    double ss = 0;
+    for (size_t i = 0; i < n; i++) ss += (y[i] - s.mean) * (y[i] - s.mean);
+    s.var_sample = n > 1 ? ss / (double)(n - 1) : 0.0;  // arma::var
+    s.tmin = t[0];
+    s.tmax = t[n - 1];
+    if (n > 1) {
+        std::vector<double> dt(n - 1);
+        for (size_t i = 0; i + 1 < n; i++) dt[i] = t[i + 1] - t[i];
+        std::sort(dt.begin(), dt.end());
+        size_t m = dt.size();
+        s.median_dt = (m % 2) ? dt[m / 2] : 0.5 * (dt[m / 2 - 1] + dt[m / 2]);
+        s.min_dt = dt[0];
+    } else {
+        s.median_dt = s.min_dt = 1.0;
+    }
+    return s;
+}
+
+void prior_from_stats(const SeriesStats& st, int population_var, carma_prior_t* out) {
+    out->max_stdev = 10.0 * std::sqrt(population_var ? st.var_pop : st.var_sample);
+    out->max_freq = 1.0 / st.min_dt;
+    out->min_freq = 1.0 / (st.tmax - st.tmin);
+    out->kappa_high = 1.0 / st.min_dt;
+    out->kappa_low = std::max(1.0 / (st.tmax - st.tmin), 1.0 / (10.0 * st.median_dt));
+    out->measerr_dof = 50.0;
+}
+
+static bool valid_model(int kind, int p, int q) {
+    if (kind < CARMA_KIND_CAR1 || kind > CARMA_KIND_ZCARMA) return false;
+    if (kind == CARMA_KIND_CAR1) return p == 1;
+    if (p < 1 || p > MAX_P) return false;
+    if (kind == CARMA_KIND_CARMA) return q >= 0 && q < p;
+    return true;
+}
+
+}  // namespace carma
+
+using namespace carma;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* carma_last_error(void) { return g_last_error.c_str(); }
+int carma_abi_version(void) { return CARMA_B200_ABI_VERSION; }
+
+int carma_device_count(int* count) {
+    if (!count) return CARMA_ERR_ARG;
+    if (!cuda_ok(cudaGetDeviceCount(count), "cudaGetDeviceCount")) { *count = 0; return CARMA_ERR_CUDA; }
+    return CARMA_OK;
+}
+
+int carma_series_create(const double* time, const double* y, const double* yerr, size_t ny, int device,
+                        carma_series_t* out) {
+    if (!time || !y || !yerr || !out || ny < 2) { set_error("carma_series_create: null pointer or ny < 2"); return CARMA_ERR_ARG; }
+    for (size_t i = 0; i + 1 < ny; i++)
+        if (!(time[i + 1] > time[i])) { set_error("carma_series_create: times must be strictly increasing"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    carma_series* s = new (std::nothrow) carma_series();
+    if (!s) return CARMA_ERR_ALLOC;
+    s->device = device;
+    s->ny = ny;
+    s->nyp = (int)((ny + 1) & ~(size_t)1);
+    s->t.assign(time, time + ny);
+    s->y.assign(y, y + ny);
+    s->yerr.assign(yerr, yerr + ny);
+    s->st = compute_stats(time, y, ny);
+    s->e2_0 = yerr[0] * yerr[0];
+    std::vector<double> pack(3 * (size_t)s->nyp + ny, 0.0);
+    for (size_t i = 0; i < ny; i++) {
+        pack[i] = (i + 1 < ny) ? time[i + 1] - time[i] : 0.0;
+        pack[s->nyp + i] = y[i];
+        pack[2 * (size_t)s->nyp + i] = (i + 1 < ny) ? yerr[i + 1] * yerr[i + 1] : 0.0;
+        pack[3 * (size_t)s->nyp + i] = time[i];
+    }
+    if (!cuda_ok(cudaMalloc((void**)&s->d_pack, pack.size() * sizeof(double)), "cudaMalloc(series)")) { delete s; return CARMA_ERR_CUDA; }
+    if (!cuda_ok(cudaMemcpy(s->d_pack, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(series)")) {
+        cudaFree(s->d_pack); delete s; return CARMA_ERR_CUDA;
+    }
+    *out = s;
+    return CARMA_OK;
+}
+
+int carma_series_destroy(carma_series_t s) {
+    if (!s) return CARMA_OK;
+    cudaSetDevice(s->device);
+    if (s->d_pack) cudaFree(s->d_pack);
+    s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release();
+    delete s;
+    return CARMA_OK;
+}
+
+int carma_series_length(carma_series_t s, size_t* ny) {
+    if (!s || !ny) return CARMA_ERR_ARG;
+    *ny = s->ny;
+    return CARMA_OK;
+}
+
+int carma_series_default_prior(carma_series_t s, int population_var, carma_prior_t* out) {
+    if (!s || !out) return CARMA_ERR_ARG;
+    prior_from_stats(s->st, population_var, out);
+    return CARMA_OK;
+}
+
+int carma_loglik_batch_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                           const double* d_theta, double* d_logpost, unsigned flags, void* stream) {
+    if (!s || !prior || (!d_theta && n) || (!d_logpost && n)) { set_error("carma_loglik_batch_dev: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_loglik_batch_dev: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    if (!cuda_ok(launch_loglik_batch(s->view(), kind, p, q, flags, *prior, d_theta, d_logpost, n, (cudaStream_t)stream),
+                 "loglik_batch_kernel launch"))
+        return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                       const double* theta, double* logpost, unsigned flags) {
+    if (!s || !prior || (!theta && n) || (!logpost && n)) { set_error("carma_loglik_batch: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_loglik_batch: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    size_t d = (size_t)model_dim(kind, p, q);
+    if (!s->scratch_in.reserve(n * d * sizeof(double)) || !s->scratch_out.reserve(n * sizeof(double))) return CARMA_ERR_CUDA;
+    cudaStream_t st = 0;
+    if (!cuda_ok(cudaMemcpyAsync(s->scratch_in.p, theta, n * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
+    int rc = carma_loglik_batch_dev(s, kind, p, q, prior, n, (const double*)s->scratch_in.p, (double*)s->scratch_out.p, flags, st);
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpyAsync(logpost, s->scratch_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaStreamSynchronize(st), "loglik_batch sync")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out) {
+    if (!theta || !prior || !out) return CARMA_ERR_ARG;
+    double scale = theta[1];
+    double lp = -0.5 * prior->measerr_dof / scale - (1.0 + prior->measerr_dof / 2.0) * std::log(scale);
+    if (kind == CARMA_KIND_ZCARMA) {
+        double x = theta[3 + p];
+        lp += -x - 2.0 * std::log(1.0 + std::exp(-x));
+    }
+    *out = lp;
+    return CARMA_OK;
+}
+
+// ---- multi-series ---------------------------------------------------------------------------
+int carma_multi_series_create(const double* time, const double* y, const double* yerr, const int64_t* offsets,
+                              size_t ncurves, int device, carma_multi_series_t* out) {
+    if (!time || !y || !yerr || !offsets || !out || ncurves == 0) { set_error("carma_multi_series_create: null argument"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    size_t total = (size_t)offsets[ncurves];
+    carma_multi_series* m = new (std::nothrow) carma_multi_series();
+    if (!m) return CARMA_ERR_ALLOC;
+    m->device = device; m->ncurves = ncurves; m->total = total;
+    m->off.assign(offsets, offsets + ncurves + 1);
+    m->priors_pop.resize(ncurves); m->priors_sample.resize(ncurves);
+    std::vector<double> dt(total + 1, 0.0), e2(total + 1, 0.0);
+    for (size_t c = 0; c < ncurves; c++) {
+        size_t o0 = (size_t)offsets[c], o1 = (size_t)offsets[c + 1];
+        if (o1 < o0 + 2) { set_error("carma_multi_series_create: every curve needs >= 2 points"); delete m; return CARMA_ERR_ARG; }
+        m->max_ny = std::max(m->max_ny, (int)(o1 - o0));
+        for (size_t i = o0; i < o1; i++) {
+            if (i + 1 < o1) {
+                dt[i] = time[i + 1] - time[i];
+                if (!(dt[i] > 0)) { set_error("carma_multi_series_create: times must be strictly increasing within a curve"); delete m; return CARMA_ERR_ARG; }
+            }
+            e2[i] = yerr[i] * yerr[i];
+        }
+        SeriesStats st = compute_stats(time + o0, y + o0, o1 - o0);
+        prior_from_stats(st, 1, &m->priors_pop[c]);
+        prior_from_stats(st, 0, &m->priors_sample[c]);
+    }
+    bool ok = cuda_ok(cudaMalloc((void**)&m->d_dt, (total + 1) * sizeof(double)), "cudaMalloc(multi dt)") &&
+              cuda_ok(cudaMalloc((void**)&m->d_y, (total + 1) * sizeof(double)), "cudaMalloc(multi y)") &&
+              cuda_ok(cudaMalloc((void**)&m->d_e2, (total + 1) * sizeof(double)), "cudaMalloc(multi e2)") &&
+              cuda_ok(cudaMalloc((void**)&m->d_off, (ncurves + 1) * sizeof(long long)), "cudaMalloc(multi off)") &&
+              cuda_ok(cudaMemcpy(m->d_dt, dt.data(), total * sizeof(double), cudaMemcpyHostToDevice), "H2D dt") &&
+              cuda_ok(cudaMemcpy(m->d_y, y, total * sizeof(double), cudaMemcpyHostToDevice), "H2D y") &&
+              cuda_ok(cudaMemcpy(m->d_e2, e2.data(), total * sizeof(double), cudaMemcpyHostToDevice), "H2D e2") &&
+              cuda_ok(cudaMemcpy(m->d_off, m->off.data(), (ncurves + 1) * sizeof(long long), cudaMemcpyHostToDevice), "H2D off");
+    if (!ok) { carma_multi_series_destroy(m); return CARMA_ERR_CUDA; }
+    *out = m;
+    return CARMA_OK;
+}
+
+int carma_multi_series_destroy(carma_multi_series_t m) {
+    if (!m) return CARMA_OK;
+    cudaSetDevice(m->device);
+    if (m->d_dt) cudaFree(m->d_dt);
+    if (m->d_y) cudaFree(m->d_y);
+    if (m->d_e2) cudaFree(m->d_e2);
+    if (m->d_off) cudaFree(m->d_off);
+    m->scratch_in.release(); m->scratch_out.release(); m->scratch_pr.release();
+    delete m;
+    return CARMA_OK;
+}
+
+int carma_multi_series_default_priors(carma_multi_series_t m, int population_var, carma_prior_t* out) {
+    if (!m || !out) return CARMA_ERR_ARG;
+    const std::vector<carma_prior_t>& src = population_var ? m->priors_pop : m->priors_sample;
+    std::memcpy(out, src.data(), src.size() * sizeof(carma_prior_t));
+    return CARMA_OK;
+}
+
+int carma_multi_loglik_dev(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* d_priors,
+                           const double* d_theta, double* d_logpost, unsigned flags, void* stream) {
+    if (!m || !d_priors || !d_theta || !d_logpost) { set_error("carma_multi_loglik_dev: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_multi_loglik_dev: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(launch_multi_loglik(m, kind, p, q, flags, d_priors, d_theta, d_logpost, (cudaStream_t)stream), "multi_loglik_kernel launch"))
+        return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_multi_loglik(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,
+                       const double* theta, double* logpost, unsigned flags) {
+    if (!m || !theta || !logpost) { set_error("carma_multi_loglik: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_multi_loglik: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    size_t d = (size_t)model_dim(kind, p, q), n = m->ncurves;
+    if (!m->scratch_in.reserve(n * d * sizeof(double)) || !m->scratch_out.reserve(n * sizeof(double)) ||
+        !m->scratch_pr.reserve(n * sizeof(carma_prior_t)))
+        return CARMA_ERR_CUDA;
+    const carma_prior_t* hp = priors ? priors : m->priors_pop.data();
+    cudaStream_t st = 0;
+    if (!cuda_ok(cudaMemcpyAsync(m->scratch_pr.p, hp, n * sizeof(carma_prior_t), cudaMemcpyHostToDevice, st), "H2D priors")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpyAsync(m->scratch_in.p, theta, n * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
+    int rc = carma_multi_loglik_dev(m, kind, p, q, (const carma_prior_t*)m->scratch_pr.p, (const double*)m->scratch_in.p,
+                                    (double*)m->scratch_out.p, flags, st);
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpyAsync(logpost, m->scratch_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaStreamSynchronize(st), "multi_loglik sync")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+// ---- explicit-parameter filter / predict ------------------------------------------------------
+static int fill_filter_args(FilterArgs& a, double sigsqr, const double* omega_reim, const double* ma, int p,
+                            double measerr_scale, double mu) {
+    if (!omega_reim || !ma || p < 1 || p > MAX_P) { set_error("filter: invalid omega/ma/p"); return CARMA_ERR_ARG; }
+    a.sigsqr = sigsqr; a.scale = measerr_scale; a.mu = mu; a.p = p;
+    for (int i = 0; i < 2 * MAX_P; i++) a.omega[i] = i < 2 * p ? omega_reim[i] : 0.0;
+    for (int i = 0; i < MAX_P; i++) a.ma[i] = i < p ? ma[i] : 0.0;
+    return CARMA_OK;
+}
+
+int carma_filter(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
+                 double measerr_scale, double mu, double* mean, double* var) {
+    if (!s || !mean || !var) { set_error("carma_filter: null argument"); return CARMA_ERR_ARG; }
+    FilterArgs a;
+    int rc = fill_filter_args(a, sigsqr, omega_reim, ma, p, measerr_scale, mu);
+    if (rc) return rc;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    size_t ny = s->ny;
+    if (!s->scratch_out.reserve((2 * ny + 2) * sizeof(double))) return CARMA_ERR_CUDA;
+    double* d_mean = (double*)s->scratch_out.p;
+    double* d_var = d_mean + ny;
+    int* d_status = (int*)(d_var + ny);
+    filter_kernel<<<1, 32>>>(s->view(), a, d_mean, d_var, d_status);
+    if (!cuda_ok(cudaGetLastError(), "filter_kernel launch")) return CARMA_ERR_CUDA;
+    int status = 0;
+    if (!cuda_ok(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost), "D2H status")) return CARMA_ERR_CUDA;
+    if (status) {
+        // singular Vandermonde system: the reference throws from arma::solve (kfilter.cpp:158)
+        for (size_t i = 0; i < ny; i++) { mean[i] = std::numeric_limits<double>::quiet_NaN(); var[i] = mean[i]; }
+        return CARMA_OK;
+    }
+    if (!cuda_ok(cudaMemcpy(mean, d_mean, ny * sizeof(double), cudaMemcpyDeviceToHost), "D2H mean")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(var, d_var, ny * sizeof(double), cudaMemcpyDeviceToHost), "D2H var")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_predict(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
+                  double measerr_scale, double mu, const double* tq, size_t nq, double* qmean, double* qvar) {
+    if (!s || !tq || !qmean || !qvar) { set_error("carma_predict: null argument"); return CARMA_ERR_ARG; }
+    if (nq == 0) return CARMA_OK;
+    FilterArgs a;
+    int rc = fill_filter_args(a, sigsqr, omega_reim, ma, p, measerr_scale, mu);
+    if (rc) return rc;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    if (!s->scratch_in.reserve(nq * sizeof(double)) || !s->scratch_out.reserve((2 * nq + 2) * sizeof(double))) return CARMA_ERR_CUDA;
+    double* d_tq = (double*)s->scratch_in.p;
+    double* d_m = (double*)s->scratch_out.p;
+    double* d_v = d_m + nq;
+    int* d_status = (int*)(d_v + nq);
+    if (!cuda_ok(cudaMemset(d_status, 0, sizeof(int)), "memset status")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(d_tq, tq, nq * sizeof(double), cudaMemcpyHostToDevice), "H2D tq")) return CARMA_ERR_CUDA;
+    unsigned grid = (unsigned)((nq + 31) / 32);
+    predict_kernel<<<grid, 32>>>(s->view(), a, d_tq, nq, d_m, d_v, d_status);
+    if (!cuda_ok(cudaGetLastError(), "predict_kernel launch")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(qmean, d_m, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qmean")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(qvar, d_v, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qvar")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+// ---- utilities --------------------------------------------------------------------------------
+int carma_fp64_peak_tflops(int device, double* tflops) {
+    if (!tflops) return CARMA_ERR_ARG;
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) return CARMA_ERR_CUDA;
+    double* d_out = nullptr;
+    if (!cuda_ok(cudaMalloc((void**)&d_out, sizeof(double)), "cudaMalloc")) return CARMA_ERR_CUDA;
+    int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, 1 << 12, 1.0000001, 1e-9);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
+        cudaEventRecord(e1);
+        if (!cuda_ok(cudaEventSynchronize(e1), "dfma_peak sync")) { cudaFree(d_out); return CARMA_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return CARMA_OK;
+}
+
+int carma_philox_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out4) {
+    if (!out4) return CARMA_ERR_ARG;
+    uint32_t* d = nullptr;
+    if (!cuda_ok(cudaMalloc((void**)&d, 4 * sizeof(uint32_t)), "cudaMalloc")) return CARMA_ERR_CUDA;
+    philox_kernel<<<1, 1>>>(c0, c1, c2, c3, seed, d);
+    bool ok = cuda_ok(cudaMemcpy(out4, d, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost), "philox D2H");
+    cudaFree(d);
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+int carma_tdist_dev(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, int dof, double* out) {
+    if (!out) return CARMA_ERR_ARG;
+    double* d = nullptr;
+    if (!cuda_ok(cudaMalloc((void**)&d, sizeof(double)), "cudaMalloc")) return CARMA_ERR_CUDA;
+    tdist_kernel<<<1, 1>>>(seed, chain, iter, j, dof, d);
+    bool ok = cuda_ok(cudaMemcpy(out, d, sizeof(double), cudaMemcpyDeviceToHost), "tdist D2H");
+    cudaFree(d);
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+}  // extern "C"

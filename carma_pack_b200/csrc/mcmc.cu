@@ -1,0 +1,553 @@
+// mcmc.cu -- K3: persistent parallel-tempering MCMC kernel.  Everything of one MCMC run happens in
+// ONE kernel launch: starting values, robust-adaptive-Metropolis proposals (Student-t_8 draws from
+// Philox), the Kalman log-density of every proposal, accept/reject, the Robbins-Monro rank-1
+// Cholesky adaptation, the tempered-chain exchanges and the storage of the coolest chain.  There is
+// no host round trip per iteration.
+//
+// Reference behaviour restated (paths relative to /root/reference/src):
+//   RunCarmaSampler / RunCar1Sampler   carmcmc.cpp:30-177   ladder, initial proposal covariance, step order
+//   Sampler::Run / Iterate             samplers.cpp:37-115  start values, burn-in, thinning, sample storage
+//   AdaptiveMetro::DoStep / Accept     steps.cpp:36-107
+//   CholUpdateR1                       steps.cpp:111-131
+//   ExchangeStep::DoStep               steps.hpp:318-362
+//   CARp/CARMA/ZCARMA/CAR1::StartingValue, StartingAR, StartingMA   carpack.cpp:38-83, 175-230, 268-311,
+//                                                                   416-477, 515-519, 586-644, 681-684
+//
+// Thread mapping: one thread = one chain = (ensemble, temperature).  All chains of an ensemble sit in
+// one block; the light curve is staged once per block in shared memory (TMA bulk copy) and stays
+// resident for the whole run.
+//
+// Step order.  The reference runs, per iteration, RAM(T-1), X(T-1,T-2), RAM(T-2), ..., X(1,0), RAM(0)
+// sequentially (carmcmc.cpp:147-157).  order_mode 0 reproduces exactly that dependency graph as a
+// skewed pipeline: at tick k chain i performs its RAM step of iteration n = k - (T-1-i); at the end of
+// the tick the exchanges X(c,c-1) of the chains that just stepped are applied from the coldest pair up.
+// Every RAM/exchange step sees precisely the state it would see in the sequential order, and all T
+// filters of an ensemble run concurrently.  Random numbers are addressed, not consumed, so the
+// evaluation order does not matter.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kalman_real.cuh"
+#include "series.h"
+
+namespace carma {
+
+constexpr int PT_BLOCK = 64;
+
+struct PTParams {
+    int kind, q, d;
+    carma_prior_t prior;
+    int nsamples, burnin, thin, T, total_iters;
+    double tmax;
+    int dof;
+    double target, gamma;
+    unsigned long long seed;
+    unsigned ens_offset;
+    int max_start, order_mode, record;
+    unsigned long long n_ens;
+    // series statistics for the starting values
+    double y_mean, y_var_sample, y_var_pop, median_dt, tspan;
+    int ny;
+    // device buffers
+    const double* init;  // d values or nullptr
+    double* samples;     // [n_ens][nsamples][d]
+    double* logposts;    // [n_ens][nsamples]
+    double* accept_rates;    // [n_ens][T] or nullptr
+    double* exchange_rates;  // [n_ens][T] or nullptr
+    double* chol;            // [ntri][nthreads_total] packed upper factors
+    carma_pt_trace_rec_t* ram_trace;   // [n_ens][iters][T]
+    carma_pt_trace_rec_t* exch_trace;  // [n_ens][iters][T]
+    double* proposals;                 // [n_ens][iters][T][d]
+    int* status;                       // !=0 : a chain found no finite starting value
+};
+
+// ---- starting-value RNG (mirrors oracle StartRng draw for draw) ---------------------------------
+struct StartRng {
+    unsigned long long seed;
+    uint32_t chain, attempt, blk;
+    __device__ void next2(double* u0, double* u1) { uniforms2(seed, chain, STREAM_START, attempt, blk++, u0, u1); }
+    __device__ double uniform() { double a, b; next2(&a, &b); return a; }
+    __device__ double normal() { double a, b; next2(&a, &b); return normal_from(a, b); }
+    __device__ double chisqr(int dof) {
+        double acc = 0.0, prod = 1.0;
+        int pairs = dof / 2, inprod = 0;
+        for (int i = 0; i < pairs; i += 2) {
+            double a, b;
+            next2(&a, &b);
+            prod *= a; inprod++;
+            if (i + 1 < pairs) { prod *= b; inprod++; }
+            if (inprod >= 8) { acc += -2.0 * log(prod); prod = 1.0; inprod = 0; }
+        }
+        if (inprod > 0) acc += -2.0 * log(prod);
+        if (dof & 1) { double z = normal(); acc += z * z; }
+        return acc;
+    }
+    __device__ double scaled_inverse_chisqr(int dof, double ssqr) { return ssqr / chisqr(dof) * (double)dof; }
+};
+
+// carpack.cpp:268-311
+template <int P>
+__device__ void starting_ar(StartRng& g, const PTParams& pp, double* loga) {
+    constexpr int NL = (P + 1) / 2;
+    constexpr double PI = 3.14159265358979323846;
+    const double min_freq = 1.0 / pp.tspan;
+    const double lr = log(pp.prior.max_freq / min_freq), l0 = log(min_freq);
+    double cent[NL], width[NL];
+    for (int i = 0; i < NL; i++) cent[i] = exp(lr * g.uniform() + l0);
+    for (int i = 1; i < NL; i++) {  // sort descending
+        double v = cent[i];
+        int j = i - 1;
+        while (j >= 0 && cent[j] < v) { cent[j + 1] = cent[j]; j--; }
+        cent[j + 1] = v;
+    }
+    for (int i = 0; i < NL; i++) width[i] = exp(lr * g.uniform() + l0);
+    if (P & 1) {
+        cent[P / 2] = 0.0;
+        double hi = (P / 2 >= 1) ? log(cent[(P / 2 >= 1) ? P / 2 - 1 : 0]) : log(pp.prior.max_freq);
+        width[P / 2] = exp(l0 + (hi - l0) * g.uniform());
+    }
+    for (int i = 0; i < P / 2; i++) {
+        double re = -2.0 * PI * width[i], im = 2.0 * PI * cent[i];
+        loga[2 * i] = log(re * re + im * im);
+        loga[2 * i + 1] = log(-2.0 * re);
+    }
+    if (P & 1) loga[P - 1] = log(2.0 * PI * width[P / 2]);
+}
+
+template <int P>
+__device__ double logdensity_resident(const PTParams& pp, const double* th, const double* sdt, const double* sy,
+                                      const double* se, double e2_0) {
+    RealParams<P> prm;
+    if (transform_theta<P>(pp.kind, pp.q, 0u, pp.prior, th, prm) != TT_OK) return -INFINITY;
+    KalmanReal<P> kf;
+    LogLikAcc acc;
+    kf.reset(prm, e2_0);
+    acc.init();
+    filter_span<P>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+    return acc.value() + prm.logprior;
+}
+
+template <int P>
+__device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double* th, const double* sdt,
+                                         const double* sy, const double* se, double e2_0) {
+    const int n = pp.ny;
+    if (pp.kind == CARMA_KIND_CAR1) {
+        double sd = sqrt(g.scaled_inverse_chisqr(n - 1, pp.y_var_sample));
+        double mu = pp.y_mean + (sd / (double)n) * g.normal();
+        double log_omega = -log(pp.median_dt * (1.0 + 49.0 * g.uniform()));
+        log_omega = fmin(log_omega, pp.prior.max_freq);  // sic (carpack.cpp:56)
+        double scale = g.scaled_inverse_chisqr((int)pp.prior.measerr_dof, 1.0);
+        scale = fmax(fmin(scale, 1.99), 0.51);
+        th[0] = sd; th[1] = scale; th[2] = mu; th[3] = log_omega;
+        return logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
+    }
+    starting_ar<P>(g, pp, th + 3);
+    if (pp.kind == CARMA_KIND_CARMA)
+        for (int i = 0; i < pp.q; i++) th[3 + P + i] = fabs(g.normal());
+    if (pp.kind == CARMA_KIND_ZCARMA) {
+        double u = g.uniform();
+        th[3 + P] = log(u / (1.0 - u));
+    }
+    double yvar = g.scaled_inverse_chisqr(n - 1, pp.y_var_sample);
+    double mu = pp.y_mean + (sqrt(yvar) / (double)n) * g.normal();
+    double scale = g.scaled_inverse_chisqr((int)pp.prior.measerr_dof, 1.0);
+    scale = fmax(fmin(scale, 1.99), 0.51);
+    th[0] = sqrt(yvar); th[1] = scale; th[2] = mu;
+    return logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
+}
+
+__device__ __forceinline__ int tri(int k, int j) { return j * (j + 1) / 2 + k; }  // k <= j
+
+template <int P>
+__global__ void __launch_bounds__(PT_BLOCK) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int T = pp.T, d = pp.d;
+    const int epb = PT_BLOCK / T;
+    const int e_local = tid / T, i = tid % T;
+    const unsigned long long ens = (unsigned long long)blockIdx.x * epb + e_local;
+    const bool active = (e_local < epb) && (ens < pp.n_ens);
+    const size_t gtid = (size_t)blockIdx.x * PT_BLOCK + tid;
+
+    // ---- stage the light curve once (TMA bulk copy), resident for the whole run
+    double* sdt = smem;
+    double* sy = smem + sv.nyp;
+    double* se = smem + 2 * (size_t)sv.nyp;
+    double* xth = smem + 3 * (size_t)sv.nyp;            // [PT_BLOCK][d] exchange area
+    double* xlp = xth + (size_t)PT_BLOCK * d;           // [PT_BLOCK]
+    double* xu = xlp + PT_BLOCK;                        // [PT_BLOCK] exchange uniforms
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // pieces of at most 64 KiB keep every transaction count far below the mbarrier tx limit
+        const uint32_t total = (uint32_t)(3 * (size_t)sv.nyp * 8);
+        mbar_expect_tx(&bar, total);
+        const uint32_t piece = 1u << 16;
+        for (uint32_t o = 0; o < total; o += piece) {
+            uint32_t b = min(piece, total - o);
+            bulk_g2s((char*)smem + o, (const char*)sv.dt + o, b, &bar);
+        }
+    }
+    mbar_wait(&bar, 0);
+
+    const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + i);
+    const double temp = (T > 1) ? exp(log(pp.tmax) * (double)i / (double)(T - 1)) : 1.0;  // carmcmc.cpp:92-95
+
+    double th[MAX_D];
+    double lp = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAX_D; j++) th[j] = 0.0;
+    int naccept = 0, nx_try = 0, nx_acc = 0;
+
+    // ---- initial proposal Cholesky factor (carmcmc.cpp:127-136; diagonal, so R = sqrt(diag))
+    double* R = pp.chol + gtid;
+    if (active) {
+        for (int j = 0; j < d; j++)
+            for (int k = 0; k <= j; k++) R[(size_t)tri(k, j) * chol_stride] = 0.0;
+        for (int j = 0; j < d; j++) R[(size_t)tri(j, j) * chol_stride] = 0.01;
+        R[(size_t)tri(0, 0) * chol_stride] = sqrt(2.0 * pp.y_var_pop * pp.y_var_pop / (double)pp.ny);
+        R[(size_t)tri(2, 2) * chol_stride] = sqrt(pp.y_var_pop / (double)pp.ny);
+    }
+
+    // ---- starting values (samplers.cpp:75-93)
+    if (active) {
+        bool ok = false;
+        if (pp.init) {
+            for (int j = 0; j < d; j++) th[j] = pp.init[j];
+            lp = logdensity_resident<P>(pp, th, sdt, sy, se, sv.e2_0);
+            ok = isfinite(lp);
+        }
+        if (!ok) {
+            for (int a = 0; a < pp.max_start && !ok; a++) {
+                StartRng g{pp.seed, chain, (uint32_t)a, 0u};
+                lp = starting_value_attempt<P>(pp, g, th, sdt, sy, se, sv.e2_0);
+                ok = isfinite(lp);
+            }
+        }
+        if (!ok) atomicExch(pp.status, 1);
+    }
+
+    const int total = pp.total_iters;
+    const int nticks = pp.order_mode == 0 ? total + T - 1 : total;
+
+    for (int tick = 0; tick < nticks; tick++) {
+        const int n = pp.order_mode == 0 ? tick - (T - 1 - i) : tick;
+        const bool stepping = active && n >= 0 && n < total;
+        if (stepping) {
+            // ---- AdaptiveMetro::DoStep (steps.cpp:60-107)
+            double z[MAX_D], sp[MAX_D], nv[MAX_D];
+            double znorm2 = 0.0;
+            for (int j = 0; j < d; j++) {
+                z[j] = tdist_draw(pp.seed, chain, STREAM_PROPOSAL, (uint32_t)n, (uint32_t)j, pp.dof);
+                znorm2 += z[j] * z[j];
+            }
+            for (int j = 0; j < d; j++) {  // chol_factor_.t() * unit_proposal
+                double s = 0.0;
+                for (int k = 0; k <= j; k++) s += R[(size_t)tri(k, j) * chol_stride] * z[k];
+                sp[j] = s;
+                nv[j] = th[j] + s;
+            }
+            for (int j = d; j < MAX_D; j++) nv[j] = 0.0;
+            const double lpn = logdensity_resident<P>(pp, nv, sdt, sy, se, sv.e2_0);
+            // ---- Accept (steps.cpp:36-56)
+            double alpha = (lpn - lp) / temp;
+            double u = NAN;
+            bool acc = false;
+            if (!isfinite(alpha)) {
+                alpha = 0.0;
+            } else {
+                double u1;
+                uniforms2(pp.seed, chain, STREAM_ACCEPT, (uint32_t)n, 0u, &u, &u1);
+                alpha = fmin(exp(alpha), 1.0);
+                if (u < alpha) { acc = true; naccept++; }
+            }
+            if (pp.record) {
+                size_t r = ((size_t)ens * total + n) * T + i;
+                carma_pt_trace_rec_t rec;
+                rec.lp_prop = lpn; rec.lp_cur = lp; rec.alpha = alpha; rec.u = u; rec.accepted = acc; rec.pad = 0;
+                pp.ram_trace[r] = rec;
+                for (int j = 0; j < d; j++) pp.proposals[r * d + j] = nv[j];
+            }
+            if (acc) {
+                for (int j = 0; j < d; j++) th[j] = nv[j];
+                lp = lpn;
+            }
+            // ---- scale-matrix adaptation while niter < burnin (steps.cpp:82-99)
+            if (n < pp.burnin) {
+                double step = fmin(1.0, (double)d / pow((double)n, pp.gamma));
+                double f = sqrt(step * fabs(alpha - pp.target)) / sqrt(znorm2);
+                const double sign = (alpha < pp.target) ? -1.0 : 1.0;
+                for (int j = 0; j < d; j++) sp[j] = f * sp[j];
+                for (int k = 0; k < d; k++) {  // CholUpdateR1 (steps.cpp:111-131)
+                    double lkk = R[(size_t)tri(k, k) * chol_stride];
+                    double r = sqrt(lkk * lkk + sign * sp[k] * sp[k]);
+                    double c = r / lkk;
+                    double s = sp[k] / lkk;
+                    R[(size_t)tri(k, k) * chol_stride] = r;
+                    for (int j = k + 1; j < d; j++) {
+                        double lkj = (R[(size_t)tri(k, j) * chol_stride] + sign * s * sp[j]) / c;
+                        R[(size_t)tri(k, j) * chol_stride] = lkj;
+                        sp[j] = c * sp[j] - s * lkj;
+                    }
+                }
+            }
+            // exchange uniform of ExchangeStep(i) at this iteration (drawn unconditionally, steps.hpp:337)
+            if (i > 0) {
+                double u0, u1;
+                uniforms2(pp.seed, chain, STREAM_EXCHANGE, (uint32_t)n, 0u, &u0, &u1);
+                xu[tid] = u0;
+            }
+            // order_mode 0: chain 0 finished iteration n -> store before this tick's exchanges
+            if (pp.order_mode == 0 && i == 0 && n >= pp.burnin && ((n - pp.burnin + 1) % pp.thin) == 0) {
+                int sidx = (n - pp.burnin + 1) / pp.thin - 1;
+                if (sidx < pp.nsamples) {
+                    size_t o = (size_t)ens * pp.nsamples + sidx;
+                    for (int j = 0; j < d; j++) pp.samples[o * d + j] = th[j];
+                    pp.logposts[o] = lp;
+                }
+            }
+        }
+        if (T > 1) {
+            // ---- exchanges (steps.hpp:318-362) through shared memory
+            if (active) {
+                for (int j = 0; j < d; j++) xth[(size_t)tid * d + j] = th[j];
+                xlp[tid] = lp;
+            }
+            __syncthreads();
+            if (active && i == 0) {
+                const int base = tid;  // thread of chain 0 of this ensemble
+                for (int s = 1; s < T; s++) {
+                    // order_mode 0: coldest pair first; order_mode 1: hottest first (reference order)
+                    const int c = pp.order_mode == 0 ? s : T - s;
+                    const int nc = pp.order_mode == 0 ? tick - (T - 1 - c) : tick;
+                    if (nc < 0 || nc >= total) continue;
+                    const double tc = exp(log(pp.tmax) * (double)c / (double)(T - 1));
+                    const double tcm = exp(log(pp.tmax) * (double)(c - 1) / (double)(T - 1));
+                    const double this_lp = xlp[base + c], other_lp = xlp[base + c - 1];
+                    double a = 1.0 / tc * (other_lp - this_lp) + 1.0 / tcm * (this_lp - other_lp);
+                    a = fmin(exp(a), 1.0);
+                    if (!isfinite(a)) a = 0.0;
+                    const double ux = xu[base + c];
+                    const bool sw = ux < a;
+                    if (sw) {
+                        for (int j = 0; j < d; j++) {
+                            double tmp = xth[(size_t)(base + c) * d + j];
+                            xth[(size_t)(base + c) * d + j] = xth[(size_t)(base + c - 1) * d + j];
+                            xth[(size_t)(base + c - 1) * d + j] = tmp;
+                        }
+                        xlp[base + c] = other_lp;
+                        xlp[base + c - 1] = this_lp;
+                    }
+                    if (pp.record) {
+                        size_t r = ((size_t)ens * total + nc) * T + c;
+                        carma_pt_trace_rec_t rec;
+                        rec.lp_prop = other_lp; rec.lp_cur = this_lp; rec.alpha = a; rec.u = ux; rec.accepted = sw; rec.pad = 0;
+                        pp.exch_trace[r] = rec;
+                    }
+                    // per-pair counters live with chain 0's thread: pack into the shared area afterwards
+                    xu[base + c] = sw ? 2.0 : 3.0;  // consumed marker: 2 = swapped, 3 = tried
+                }
+            }
+            __syncthreads();
+            if (active) {
+                for (int j = 0; j < d; j++) th[j] = xth[(size_t)tid * d + j];
+                lp = xlp[tid];
+                if (i > 0 && stepping) {
+                    double m = xu[tid];
+                    if (m == 2.0) { nx_try++; nx_acc++; }
+                    else if (m == 3.0) nx_try++;
+                }
+            }
+        }
+        if (pp.order_mode == 1 && stepping && i == 0 && n >= pp.burnin && ((n - pp.burnin + 1) % pp.thin) == 0) {
+            int sidx = (n - pp.burnin + 1) / pp.thin - 1;
+            if (sidx < pp.nsamples) {
+                size_t o = (size_t)ens * pp.nsamples + sidx;
+                for (int j = 0; j < d; j++) pp.samples[o * d + j] = th[j];
+                pp.logposts[o] = lp;
+            }
+        }
+    }
+
+    if (active) {
+        if (pp.accept_rates) pp.accept_rates[(size_t)ens * T + i] = total > 0 ? (double)naccept / (double)total : 0.0;
+        if (pp.exchange_rates) pp.exchange_rates[(size_t)ens * T + i] = nx_try > 0 ? (double)nx_acc / (double)nx_try : 0.0;
+    }
+}
+
+static size_t pt_smem_bytes(const SeriesView& sv, int d) {
+    return (3 * (size_t)sv.nyp + (size_t)PT_BLOCK * d + 2 * PT_BLOCK) * sizeof(double);
+}
+
+template <int P>
+static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t chol_stride, unsigned grid,
+                             cudaStream_t stream) {
+    size_t smem = pt_smem_bytes(sv, pp.d);
+    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride);
+    return cudaGetLastError();
+}
+
+static bool valid_model_pt(int kind, int p, int q) {
+    if (kind < CARMA_KIND_CAR1 || kind > CARMA_KIND_ZCARMA) return false;
+    if (kind == CARMA_KIND_CAR1) return p == 1;
+    if (p < 1 || p > MAX_P) return false;
+    if (kind == CARMA_KIND_CARMA) return q >= 0 && q < p;
+    return true;
+}
+
+}  // namespace carma
+
+using namespace carma;
+
+extern "C" {
+
+void carma_pt_default_opts(carma_pt_opts_t* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->nsamples = 1000;
+    o->burnin = 500;
+    o->thin = 1;
+    o->ntemps = 10;
+    o->tmax = 100.0;
+    o->dof = 8;
+    o->target_rate = 0.25;
+    o->gamma = 2.0 / 3.0;
+    o->seed = 1;
+    o->ensemble_offset = 0;
+    o->max_start_attempts = 1000;
+    o->order_mode = 0;
+    o->record_trace = 0;
+}
+
+static int pt_check(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* o,
+                    const void* samples, const void* logposts, const char* who) {
+    if (!s || !prior || !o || !samples || !logposts) { set_error(std::string(who) + ": null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model_pt(kind, p, q)) { set_error(std::string(who) + ": invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (o->ntemps < 1 || o->ntemps > PT_BLOCK || o->thin < 1 || o->nsamples < 0 || o->burnin < 0 || (o->dof & 1) || o->dof < 2) {
+        set_error(std::string(who) + ": invalid options (1 <= ntemps <= 64, thin >= 1, even dof >= 2)");
+        return CARMA_ERR_ARG;
+    }
+    return CARMA_OK;
+}
+
+// Fill PTParams, reserve the Cholesky scratch (owned by the series) and launch.  All pointers are
+// device pointers.  *d_status_out receives the address of the device status word.
+static int pt_launch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* o,
+                     size_t n_ensembles, const double* d_init, double* d_samples, double* d_logposts,
+                     double* d_accept_rates, double* d_exchange_rates, carma_pt_trace_rec_t* d_rt,
+                     carma_pt_trace_rec_t* d_xt, double* d_pr, cudaStream_t st, int** d_status_out) {
+    SeriesView sv = s->view();
+    PTParams pp{};
+    pp.kind = kind; pp.q = q; pp.d = model_dim(kind, p, q);
+    pp.prior = *prior;
+    pp.nsamples = o->nsamples; pp.burnin = o->burnin; pp.thin = o->thin; pp.T = o->ntemps;
+    pp.total_iters = o->burnin + o->nsamples * o->thin;
+    pp.tmax = o->tmax; pp.dof = o->dof; pp.target = o->target_rate; pp.gamma = o->gamma;
+    pp.seed = o->seed; pp.ens_offset = o->ensemble_offset; pp.max_start = std::max(1, o->max_start_attempts);
+    pp.order_mode = o->order_mode; pp.record = (d_rt && d_xt && d_pr) ? 1 : 0;
+    pp.n_ens = n_ensembles;
+    pp.y_mean = s->st.mean; pp.y_var_sample = s->st.var_sample; pp.y_var_pop = s->st.var_pop;
+    pp.median_dt = s->st.median_dt; pp.tspan = s->st.tmax - s->st.tmin; pp.ny = (int)s->ny;
+    pp.init = d_init; pp.samples = d_samples; pp.logposts = d_logposts;
+    pp.accept_rates = d_accept_rates; pp.exchange_rates = d_exchange_rates;
+    pp.ram_trace = d_rt; pp.exch_trace = d_xt; pp.proposals = d_pr;
+    if (pt_smem_bytes(sv, pp.d) > 220 * 1024) {
+        set_error("carma_pt_run: series too long for the resident-series MCMC kernel (ny <= ~9000)");
+        return CARMA_ERR_ARG;
+    }
+    int epb = PT_BLOCK / pp.T;
+    unsigned grid = (unsigned)((n_ensembles + epb - 1) / epb);
+    size_t nthreads = (size_t)grid * PT_BLOCK;
+    size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
+    if (!s->scratch_misc.reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;
+    pp.chol = (double*)s->scratch_misc.p;
+    pp.status = (int*)((char*)s->scratch_misc.p + ntri * nthreads * sizeof(double));
+    if (d_status_out) *d_status_out = pp.status;
+    if (!cuda_ok(cudaMemsetAsync(pp.status, 0, sizeof(int), st), "memset status")) return CARMA_ERR_CUDA;
+    cudaError_t e;
+    switch (p) {
+        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st); break;
+        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st); break;
+        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st); break;
+        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st); break;
+        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st); break;
+        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st); break;
+        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st); break;
+        default: e = cudaErrorInvalidValue;
+    }
+    if (!cuda_ok(e, "pt_kernel launch")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_pt_run_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior,
+                     const carma_pt_opts_t* o, size_t n_ensembles, const double* d_init, double* d_samples,
+                     double* d_logposts, double* d_accept_rates, double* d_exchange_rates, void* stream) {
+    int rc = pt_check(s, kind, p, q, prior, o, d_samples, d_logposts, "carma_pt_run_dev");
+    if (rc) return rc;
+    if (n_ensembles == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    return pt_launch(s, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_logposts, d_accept_rates,
+                     d_exchange_rates, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr);
+}
+
+int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* o,
+                 size_t n_ensembles, const double* init, double* samples, double* logposts, double* accept_rates,
+                 double* exchange_rates, carma_pt_trace_rec_t* ram_trace, carma_pt_trace_rec_t* exch_trace,
+                 double* proposals) {
+    int rc = pt_check(s, kind, p, q, prior, o, samples, logposts, "carma_pt_run");
+    if (rc) return rc;
+    if (n_ensembles == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    const bool rec = o->record_trace && ram_trace && exch_trace && proposals;
+    const size_t d = (size_t)model_dim(kind, p, q), T = (size_t)o->ntemps;
+    const size_t iters = (size_t)o->burnin + (size_t)o->nsamples * o->thin;
+    const size_t n_s = n_ensembles * (size_t)o->nsamples;
+    const size_t n_tr = rec ? n_ensembles * iters * T : 0;
+    size_t bytes_out = (n_s * d + n_s + 2 * n_ensembles * T) * sizeof(double);
+    size_t bytes_tr = 2 * n_tr * sizeof(carma_pt_trace_rec_t) + n_tr * d * sizeof(double);
+    if (!s->scratch_out.reserve(bytes_out + bytes_tr + 64) || !s->scratch_in.reserve(d * sizeof(double))) return CARMA_ERR_CUDA;
+    double* d_samples = (double*)s->scratch_out.p;
+    double* d_lp = d_samples + n_s * d;
+    double* d_ar = d_lp + n_s;
+    double* d_xr = d_ar + n_ensembles * T;
+    carma_pt_trace_rec_t* d_rt = (carma_pt_trace_rec_t*)(d_xr + n_ensembles * T);
+    carma_pt_trace_rec_t* d_xt = d_rt + n_tr;
+    double* d_pr = (double*)(d_xt + n_tr);
+    if (!cuda_ok(cudaMemset(s->scratch_out.p, 0, bytes_out + bytes_tr), "memset outputs")) return CARMA_ERR_CUDA;
+    const double* d_init = nullptr;
+    if (init) {
+        if (!cuda_ok(cudaMemcpy(s->scratch_in.p, init, d * sizeof(double), cudaMemcpyHostToDevice), "H2D init")) return CARMA_ERR_CUDA;
+        d_init = (const double*)s->scratch_in.p;
+    }
+    int* d_status = nullptr;
+    rc = pt_launch(s, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_lp, d_ar, d_xr, rec ? d_rt : nullptr,
+                   rec ? d_xt : nullptr, rec ? d_pr : nullptr, 0, &d_status);
+    if (rc) return rc;
+    if (!cuda_ok(cudaDeviceSynchronize(), "pt_kernel")) return CARMA_ERR_CUDA;
+    int status = 0;
+    if (!cuda_ok(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost), "D2H status")) return CARMA_ERR_CUDA;
+    if (status) { set_error("carma_pt_run: a chain found no finite starting value within max_start_attempts"); return CARMA_ERR_START; }
+    bool ok = cuda_ok(cudaMemcpy(samples, d_samples, n_s * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H samples") &&
+              cuda_ok(cudaMemcpy(logposts, d_lp, n_s * sizeof(double), cudaMemcpyDeviceToHost), "D2H logposts");
+    if (ok && accept_rates) ok = cuda_ok(cudaMemcpy(accept_rates, d_ar, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H accept");
+    if (ok && exchange_rates) ok = cuda_ok(cudaMemcpy(exchange_rates, d_xr, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H exch");
+    if (ok && rec) {
+        ok = cuda_ok(cudaMemcpy(ram_trace, d_rt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost), "D2H ram trace") &&
+             cuda_ok(cudaMemcpy(exch_trace, d_xt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost), "D2H exch trace") &&
+             cuda_ok(cudaMemcpy(proposals, d_pr, n_tr * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H proposals");
+    }
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// series.h -- host-side objects behind the opaque handles of include/carma_b200.h
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/carma_b200.h"
+#include "kalman_cplx.cuh"
+
+namespace carma {
+
+struct SeriesStats {
+    double mean, var_sample, var_pop, median_dt, min_dt, tmin, tmax;
+};
+
+void set_error(const std::string& msg);
+bool cuda_ok(cudaError_t e, const char* what);
+
+// scratch device buffer that only grows
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes);
+    void release();
+};
+
+}  // namespace carma
+
+struct carma_series {
+    int device = 0;
+    size_t ny = 0;
+    int nyp = 0;
+    double* d_pack = nullptr;  // [dt | y | e2n] (3 x nyp) followed by t (ny)
+    double e2_0 = 0.0;
+    std::vector<double> t, y, yerr;
+    carma::SeriesStats st{};
+    carma::DevBuf scratch_in, scratch_out, scratch_misc;
+    carma::SeriesView view() const {
+        carma::SeriesView v;
+        v.dt = d_pack;
+        v.y = d_pack + nyp;
+        v.e2n = d_pack + 2 * (size_t)nyp;
+        v.t = d_pack + 3 * (size_t)nyp;
+        v.e2_0 = e2_0;
+        v.ny = (int)ny;
+        v.nyp = nyp;
+        return v;
+    }
+};
+
+struct carma_multi_series {
+    int device = 0;
+    size_t ncurves = 0;
+    size_t total = 0;
+    // SoA device arrays of length total (+pad): dt (to next point of the same curve, 0 at the end),
+    // y, e2 (yerr^2), and CSR offsets (ncurves+1)
+    double* d_dt = nullptr;
+    double* d_y = nullptr;
+    double* d_e2 = nullptr;
+    long long* d_off = nullptr;
+    std::vector<long long> off;
+    std::vector<carma_prior_t> priors_pop, priors_sample;
+    carma::DevBuf scratch_in, scratch_out, scratch_pr;
+    int max_ny = 0;
+};
+
+namespace carma {
+SeriesStats compute_stats(const double* t, const double* y, size_t n);
+void prior_from_stats(const SeriesStats& st, int population_var, carma_prior_t* out);
+}  // namespace carma

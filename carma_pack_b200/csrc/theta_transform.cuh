@@ -1,0 +1,260 @@
+// theta_transform.cuh -- per-theta prologue of the log-density kernels (K2 in DESIGN.md).
+//
+// theta -> AR roots, MA coefficients, sigma^2, prior bounds, log-prior, and the constants of
+// the Kalman filter in the rotated state space, reduced to its independent real half.
+//
+// Reference behaviour restated here (paths relative to /root/reference/src):
+//   CARp::ARRoots                 carpack.cpp:137-172
+//   CARp::CheckPriorBounds        carpack.cpp:314-374   (CAR1: 116-130, base: carpack.hpp:178-191)
+//   CARp::Variance                carpack.cpp:377-409
+//   CARMA::ExtractMA / polycoefs  carpack.cpp:522-580, 742-756
+//   ZCARMA::ExtractMA / LogPrior  carpack.cpp:687-698, carpack.hpp:444-456
+//   CARMA_Base::LogPrior          carpack.hpp:118-126
+//   KalmanFilterp::Reset          kfilter.cpp:138-186  (J, rotated MA coefficients b, stationary V)
+//
+// Rotated state space, real half.  The AR roots produced by ARRoots are, per quadratic factor,
+// either a complex-conjugate pair or two real roots (plus one real root when p is odd), and the MA
+// coefficients are real.  Hence the rotated state x (kfilter.cpp:194-201) satisfies
+// x_{2s+1} = conj(x_{2s}) on a conjugate pair and is real on real roots, and the covariance P has
+// only p(p+1)/2 independent real numbers.  We carry z = (Re x_{2s}, Im x_{2s}) for a conjugate pair,
+// (x_{2s}, x_{2s+1}) for a real pair, and x_{p-1} for the odd root; the observation row b becomes
+// the real row c, and Cov(z, y) under the stationary law becomes the real vector h = V b^H.
+#pragma once
+#include "../../include/carma_b200.h"
+#include "device_math.cuh"
+
+namespace carma {
+
+constexpr int MAX_P = CARMA_MAX_P;
+constexpr int MAX_D = 3 + MAX_P + MAX_P;  // >= 3+p+q and 4+p
+
+__host__ __device__ inline int model_dim(int kind, int p, int q) {
+    if (kind == CARMA_KIND_CAR1) return 4;
+    if (kind == CARMA_KIND_CARMA) return 3 + p + q;
+    if (kind == CARMA_KIND_ZCARMA) return 4 + p;
+    return 3 + p;
+}
+
+template <int P>
+struct RealParams {
+    // slot s < P/2:  conjugate pair -> lam[2s] = Re w, lam[2s+1] = Im w (of the first root, <= 0)
+    //                real pair      -> lam[2s] = w_{2s}, lam[2s+1] = w_{2s+1}
+    // odd P: lam[P-1] = w_{P-1}
+    double lam[P];
+    double c[P];  // observation row in the real basis
+    double h[P];  // stationary Cov(z, y)
+    double v0;    // stationary Var(y) = Re(b V b^H)
+    double scale, mu, logprior;
+    unsigned cmask;  // bit s set: slot s is a conjugate pair
+};
+
+enum { TT_OK = 0, TT_NEG_INF = 1 };
+
+__device__ __forceinline__ cxd cdiv_simple(cxd a, cxd b) {
+    double inv = 1.0 / (b.re * b.re + b.im * b.im);
+    return cxd{(a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv};
+}
+
+// roots of prod_s (q1_s + q2_s x + x^2) [ * (x + q_last) ]  from log quadratic terms
+template <int N>
+__device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cxd* w) {
+    unsigned cmask = 0;
+#pragma unroll
+    for (int s = 0; s < N / 2; s++) {
+        if (2 * s + 1 < n) {
+            double q1 = exp(logq[2 * s]);
+            double q2 = exp(logq[2 * s + 1]);
+            // no FMA contraction here: the sign of the discriminant selects the branch
+            double disc = __dsub_rn(__dmul_rn(q2, q2), __dmul_rn(4.0, q1));
+            if (disc > 0) {
+                double sq = sqrt(disc);
+                w[2 * s] = cx(-0.5 * (q2 + sq), 0.0);
+                w[2 * s + 1] = cx(-0.5 * (q2 - sq), 0.0);
+            } else {
+                double re = -0.5 * q2;
+                double im = -0.5 * sqrt(-disc);
+                w[2 * s] = cx(re, im);
+                w[2 * s + 1] = cx(re, -im);
+                cmask |= 1u << s;
+            }
+        }
+    }
+    if (n & 1) w[n - 1] = cx(-exp(logq[n - 1]), 0.0);
+    return cmask;
+}
+
+// Returns TT_NEG_INF when the log-density is -inf (bounds violated / singular), else TT_OK.
+template <int P>
+__device__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
+                               RealParams<P>& out) {
+    constexpr double PI = 3.14159265358979323846;
+    const double ysigma = th[0], scale = th[1];
+    out.scale = scale;
+    out.mu = th[2];
+
+    cxd w[P];
+    unsigned cmask = 0;
+    if (kind == CARMA_KIND_CAR1) {
+        // carpack.hpp:265: omega = exp(theta3); the state-space root is -omega
+        w[0] = cx(-exp(th[3]), 0.0);
+    } else {
+        cmask = quad_roots_dev<P>(th + 3, P, w);
+    }
+    out.cmask = cmask;
+
+    // ---- prior bounds
+    if (kind == CARMA_KIND_CAR1) {
+        double omega = -w[0].re;
+        if ((omega > pr.max_freq) || (omega < pr.min_freq) || (ysigma > pr.max_stdev) || (ysigma < 0) ||
+            (scale < 0.5) || (scale > 2.0))
+            return TT_NEG_INF;
+    } else if (!(flags & CARMA_IGNORE_BOUNDS)) {
+        bool ok = true;
+        double prev_cent = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            double cent = fabs(w[i].im) / 2.0 / PI;
+            double width = -w[i].re / 2.0 / PI;
+            ok = ok && (cent < pr.max_freq) && (width < pr.max_freq) && (width > pr.min_freq);
+            if (i > 0 && (cent - prev_cent > 1e-8)) ok = false;
+            prev_cent = cent;
+        }
+        if ((ysigma > pr.max_stdev) || (ysigma < 0) || (scale < 0.5) || (scale > 2.0)) ok = false;
+        // unique_roots(ar_roots, 1e-4): carpack.cpp:709-732
+        double min_frac = 100.0 * 1e-4;
+#pragma unroll
+        for (int i = 0; i < P - 1; i++)
+#pragma unroll
+            for (int j = i + 1; j < P; j++) {
+                double frac = cabs_(cdiv(w[i] - w[j], w[i] + w[j]));
+                if (frac < min_frac) min_frac = frac;
+            }
+        if (!(min_frac > 1e-4)) ok = false;
+        if (!ok) return TT_NEG_INF;
+    }
+
+    // ---- MA coefficients
+    double ma[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) ma[i] = (i == 0) ? 1.0 : 0.0;
+    if (kind == CARMA_KIND_CARMA && q > 0) {
+        cxd r[P];
+        cxd cf[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) { r[i] = cx(0, 0); cf[i] = cx(0, 0); }
+        quad_roots_dev<P>(th + 3 + P, q, r);
+        cf[0] = cx(1.0, 0.0);
+        for (int i = 0; i < q; i++)
+            for (int j = i + 1; j >= 1; j--) cf[j] = cf[j] - r[i] * cf[j - 1];
+        double norm = cf[q].re;
+        for (int i = 0; i <= q; i++) ma[i] = cf[q - i].re / norm;
+    } else if (kind == CARMA_KIND_ZCARMA) {
+        double x = th[3 + P];
+        double kn = exp(x) / (1.0 + exp(x));
+        double kappa = (pr.kappa_high - pr.kappa_low) * kn + pr.kappa_low;
+        double binom = 1.0;
+#pragma unroll
+        for (int i = 1; i < P; i++) {
+            binom = binom * (double)(P - i) / (double)i;  // C(P-1, i)
+            ma[i] = rint(binom) / pow(kappa, (double)i);
+        }
+    }
+
+    // ---- rotated MA row b_k = beta(w_k), beta(-w_k), and Variance(w, beta, sigma=1)
+    cxd b[P];
+    cxd var_acc = cx(0, 0);
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        cxd s1 = cx(ma[P - 1], 0), s2 = cx(ma[P - 1], 0);
+        cxd mw = -w[k];
+#pragma unroll
+        for (int l = P - 2; l >= 0; l--) {
+            s1 = s1 * w[k] + cx(ma[l], 0);
+            s2 = s2 * mw + cx(ma[l], 0);
+        }
+        b[k] = s1;
+        cxd dp = cx(1, 0);
+#pragma unroll
+        for (int l = 0; l < P; l++)
+            if (l != k) dp = dp * ((w[l] - w[k]) * (conj(w[l]) + w[k]));
+        cxd denom = (-2.0 * w[k].re) * dp;
+        var_acc = var_acc + cdiv(s1 * s2, denom);
+    }
+    double sigsqr;
+    if (kind == CARMA_KIND_CAR1)
+        sigsqr = 2.0 * ysigma * ysigma * (-w[0].re);  // carpack.hpp:272-274
+    else
+        sigsqr = ysigma * ysigma / var_acc.re;  // carpack.hpp:316-319, 391-395
+
+    // ---- J = E^{-1} e_p for the Vandermonde E (kfilter.cpp:144-158), closed form
+    cxd J[P];
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        cxd dp = cx(1, 0);
+#pragma unroll
+        for (int l = 0; l < P; l++)
+            if (l != k) dp = dp * (w[k] - w[l]);
+        if (dp.re == 0.0 && dp.im == 0.0) singular = true;
+        J[k] = cdiv(cx(1, 0), dp);
+    }
+    if (singular) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
+
+    // ---- stationary covariance V (kfilter.cpp:165-172), h = V b^H, v0 = Re(b V b^H)
+    cxd h[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) h[i] = cx(0, 0);
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+#pragma unroll
+        for (int j = i; j < P; j++) {
+            cxd num = (-sigsqr) * (J[i] * conj(J[j]));
+            cxd vij = cdiv_simple(num, w[i] + conj(w[j]));
+            h[i] = h[i] + vij * conj(b[j]);
+            if (j > i) h[j] = h[j] + conj(vij) * conj(b[i]);
+        }
+    }
+    double v0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; i++) v0 += b[i].re * h[i].re - b[i].im * h[i].im;
+    out.v0 = v0;
+
+    // ---- real half
+#pragma unroll
+    for (int s = 0; s < P / 2; s++) {
+        if ((cmask >> s) & 1u) {
+            out.lam[2 * s] = w[2 * s].re;
+            out.lam[2 * s + 1] = w[2 * s].im;
+            out.c[2 * s] = 2.0 * b[2 * s].re;
+            out.c[2 * s + 1] = -2.0 * b[2 * s].im;
+            out.h[2 * s] = h[2 * s].re;
+            out.h[2 * s + 1] = h[2 * s].im;
+        } else {
+            out.lam[2 * s] = w[2 * s].re;
+            out.lam[2 * s + 1] = w[2 * s + 1].re;
+            out.c[2 * s] = b[2 * s].re;
+            out.c[2 * s + 1] = b[2 * s + 1].re;
+            out.h[2 * s] = h[2 * s].re;
+            out.h[2 * s + 1] = h[2 * s + 1].re;
+        }
+    }
+    if (P & 1) {
+        out.lam[P - 1] = w[P - 1].re;
+        out.c[P - 1] = b[P - 1].re;
+        out.h[P - 1] = h[P - 1].re;
+    }
+
+    // ---- log prior (carpack.hpp:118-126, 444-456)
+    double lp = 0.0;
+    if (!(flags & CARMA_LOGLIK_ONLY)) {
+        lp = -0.5 * pr.measerr_dof / scale - (1.0 + pr.measerr_dof / 2.0) * log(scale);
+        if (kind == CARMA_KIND_ZCARMA) {
+            double x = th[3 + P];
+            lp += -x - 2.0 * log(1.0 + exp(-x));
+        }
+    }
+    out.logprior = lp;
+    return TT_OK;
+}
+
+}  // namespace carma

@@ -1,0 +1,196 @@
+/* carma_b200.h -- C ABI of the B200-native CARMA(p,q) Kalman log-likelihood / PT-MCMC path.
+ *
+ * This is the drop-in boundary for ONE hot path of brandonckelly/carma_pack:
+ *   KalmanFilterp::Reset/Update/Filter/Predict      (src/kfilter.cpp:138-337, src/include/kfilter.hpp:126-132)
+ *   CARMA_Base<>::LogDensity / LogPrior / bounds     (src/include/carpack.hpp:118-191)
+ *   CARp/CARMA/ZCARMA theta -> (roots, MA, sigma^2)  (src/carpack.cpp:137-172, 314-409, 522-580, 687-698)
+ *   AdaptiveMetro / ExchangeStep / Sampler::Run      (src/steps.cpp:24-131, src/include/steps.hpp:318-362,
+ *                                                     src/samplers.cpp:57-124, src/carmcmc.cpp:30-177)
+ * Each entry point cites the reference interface it replaces.  Plain pointers and sizes only:
+ * no C++ types, no torch types, no exceptions.  All arithmetic is FP64 on the GPU; there is no
+ * CPU fallback: every compute entry point returns CARMA_ERR_CUDA when no device is usable.
+ *
+ * Conventions
+ *   - return value: 0 = CARMA_OK, otherwise a CARMA_ERR_* code; carma_last_error() gives text.
+ *   - -inf / NaN log-densities are VALUES (prior violated, singular model), never errors
+ *     (reference: src/include/carpack.hpp:134-138, 154-164; src/steps.cpp:41-46).
+ *   - `*_dev` entry points take DEVICE pointers and a cudaStream_t (passed as void*), do no
+ *     synchronisation and no host<->device copies; the plain variants take HOST pointers,
+ *     copy in/out and synchronise before returning.
+ *   - theta rows are laid out as the reference's value_ vectors (src/include/carpack.hpp:131-176):
+ *       CAR1  : [sigma_y, measerr_scale, mu, log(omega)]                        d = 4
+ *       CARp  : [sigma_y, measerr_scale, mu, log-quad AR terms (p)]             d = 3+p
+ *       CARMA : [..., log-quad AR terms (p), log-quad MA terms (q)]             d = 3+p+q
+ *       ZCAR  : as CARp (the reference evaluates ZCAR as CAR(p)) d = 3+p
+ *       ZCARMA: [..., AR terms (p), logit(kappa_normalised)]                    d = 4+p
+ */
+#ifndef CARMA_B200_H
+#define CARMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARMA_B200_ABI_VERSION 1
+
+enum {
+    CARMA_OK = 0,
+    CARMA_ERR_ARG = 1,    /* bad argument (null pointer, p out of range, unsorted times, ...) */
+    CARMA_ERR_CUDA = 2,   /* CUDA runtime/driver failure, or no device */
+    CARMA_ERR_ALLOC = 3,  /* host or device allocation failure */
+    CARMA_ERR_START = 4   /* no finite starting value found within max_start_attempts */
+};
+
+/* model classes of src/include/carpack.hpp:251-461 */
+enum {
+    CARMA_KIND_CAR1 = 0,
+    CARMA_KIND_CARP = 1,
+    CARMA_KIND_CARMA = 2,
+    CARMA_KIND_ZCAR = 3,
+    CARMA_KIND_ZCARMA = 4
+};
+
+/* flags for the log-density entry points */
+enum {
+    CARMA_IGNORE_BOUNDS = 1u, /* SetMLE(true): skip CheckPriorBounds (src/include/carpack.hpp:180, 230) */
+    CARMA_LOGLIK_ONLY = 2u    /* do not add LogPrior (new; the reference always adds it) */
+};
+
+#define CARMA_MAX_P 7
+
+/* prior / bounds of CARMA_Base::SetPrior (src/include/carpack.hpp:201-207) and the ZCARMA kappa
+ * bounds (src/include/carpack.hpp:413-419) */
+typedef struct carma_prior {
+    double max_stdev;
+    double max_freq;
+    double min_freq;
+    double kappa_low;
+    double kappa_high;
+    double measerr_dof; /* 50, src/include/carpack.hpp:63 */
+} carma_prior_t;
+
+/* One light curve resident in HBM (time, y, yerr of KalmanFilter<>::time_/y_/yerr_,
+ * src/include/kfilter.hpp:186-190).  Opaque. */
+typedef struct carma_series* carma_series_t;
+/* A ragged batch of light curves (CSR offsets) resident in HBM. Opaque. */
+typedef struct carma_multi_series* carma_multi_series_t;
+
+const char* carma_last_error(void);
+int carma_abi_version(void);
+int carma_device_count(int* count);
+
+/* ---- series -------------------------------------------------------------------------------
+ * Replaces the data members / init() of KalmanFilter<> (src/include/kfilter.hpp:43-76) and the
+ * copies held by CARMA_Base (src/include/carpack.hpp:66-68).  Times must be strictly increasing
+ * (the reference sorts and de-duplicates in init(); the Python CarmaModel already guarantees it,
+ * src/carmcmc/carma_pack.py:32-43).  Host pointers. */
+int carma_series_create(const double* time, const double* y, const double* yerr, size_t ny, int device,
+                        carma_series_t* out);
+int carma_series_destroy(carma_series_t s);
+int carma_series_length(carma_series_t s, size_t* ny);
+/* SetPrior(10*sqrt(var(y))) with var = population variance as RunCarmaSampler does
+ * (src/carmcmc.cpp:85-89) when population_var != 0, else the N-1 variance of the class
+ * constructors (src/include/carpack.hpp:71). */
+int carma_series_default_prior(carma_series_t s, int population_var, carma_prior_t* out);
+
+/* ---- hot path: batched CARMA_Base::LogDensity ----------------------------------------------
+ * Replaces n calls of Parameter<arma::vec>::LogDensity(theta) (src/include/carpack.hpp:131-176,
+ * called from src/steps.cpp:39 and src/boost_python_wrapper.cpp:51-72 getLogDensity).
+ * theta: n x d row-major; logpost: n. */
+int carma_loglik_batch_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                           const double* d_theta, double* d_logpost, unsigned flags, void* stream);
+int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                       const double* theta, double* logpost, unsigned flags);
+/* CARMA_Base::getLogPrior (src/include/carpack.hpp:221-225): host-side scalar helper. */
+int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out);
+
+/* ---- multi light-curve batch (one theta per curve) ----------------------------------------
+ * The reference loops over objects in Python; this is the survey-scale form of the same
+ * LogDensity call.  offsets: ncurves+1 (CSR), host pointers. priors: ncurves or NULL (defaults). */
+int carma_multi_series_create(const double* time, const double* y, const double* yerr, const int64_t* offsets,
+                              size_t ncurves, int device, carma_multi_series_t* out);
+int carma_multi_series_destroy(carma_multi_series_t m);
+int carma_multi_series_default_priors(carma_multi_series_t m, int population_var, carma_prior_t* out /* ncurves */);
+int carma_multi_loglik_dev(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* d_priors,
+                           const double* d_theta /* ncurves x d */, double* d_logpost, unsigned flags, void* stream);
+int carma_multi_loglik(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,
+                       const double* theta, double* logpost, unsigned flags);
+
+/* ---- explicit-parameter filter: KalmanFilterp / KalmanFilter1 ------------------------------
+ * Replaces KalmanFilterp(t,y,yerr,sigsqr,omega,ma).Filter() + GetMean()/GetVar()
+ * (src/include/kfilter.hpp:303-334, 116-117; src/kfilter.cpp:138-215).  omega_reim: p complex roots as
+ * (re,im) pairs in any order; ma: p coefficients.  The stored series is used as  y - mu  with
+ * yerr*sqrt(measerr_scale) (pass mu=0, measerr_scale=1 for the raw class semantics).  For p == 1
+ * this is KalmanFilter1 with omega_reim = (-omega, 0).  Outputs are host arrays of length ny. */
+int carma_filter(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
+                 double measerr_scale, double mu, double* mean, double* var);
+/* Replaces nq calls of KalmanFilterp::Predict(time) (src/kfilter.cpp:218-286 with
+ * InitializeCoefs/UpdateCoefs 290-337): forecasting, backcasting and interpolation. */
+int carma_predict(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
+                  double measerr_scale, double mu, const double* tq, size_t nq, double* qmean, double* qvar);
+
+/* ---- parallel-tempering MCMC, fully on device ---------------------------------------------
+ * Replaces RunCarmaSampler / RunCar1Sampler (src/carmcmc.cpp:30-177): temperature ladder,
+ * AdaptiveMetro (src/steps.cpp:24-107), CholUpdateR1 (111-131), ExchangeStep
+ * (src/include/steps.hpp:318-362) and Sampler::Run (src/samplers.cpp:57-115), for n_ensembles
+ * independent ensembles on one series.  Random numbers are Philox4x32-10 addressed by
+ * (seed, stream, chain = (ensemble_offset+e)*ntemps + temperature, iteration, slot). */
+typedef struct carma_pt_opts {
+    int nsamples;            /* stored samples of the coolest chain */
+    int burnin;              /* iterations before sampling; adaptation stops after burnin */
+    int thin;
+    int ntemps;              /* nwalkers of RunCarmaSampler */
+    double tmax;             /* 100  (src/carmcmc.cpp:92) */
+    int dof;                 /* 8    (src/carmcmc.cpp:139), must be even */
+    double target_rate;      /* 0.25 (src/carmcmc.cpp:141) */
+    double gamma;            /* 2/3  (src/steps.cpp:29) */
+    uint64_t seed;
+    uint32_t ensemble_offset; /* global index of the first ensemble (multi-GPU sharding) */
+    int max_start_attempts;  /* cap of the redraw-until-finite loop (src/carpack.cpp:182-227) */
+    int order_mode;          /* 0 = reference step order (src/carmcmc.cpp:147-157), evaluated as a
+                                skewed pipeline that is exactly equivalent; 1 = all temperatures
+                                propose concurrently, then sequential exchanges (valid PT, not
+                                decision-identical to the reference) */
+    int record_trace;        /* 0/1: fill the trace arrays of carma_pt_run (parity tests) */
+} carma_pt_opts_t;
+
+typedef struct carma_pt_trace_rec {
+    double lp_prop;  /* LogDensity(proposal)            (exchange: log-posterior of the colder chain) */
+    double lp_cur;   /* cached log-posterior before the step */
+    double alpha;    /* acceptance probability (0 if non-finite, src/steps.cpp:41-46) */
+    double u;        /* uniform used; NaN if none was drawn */
+    int accepted;
+    int pad;
+} carma_pt_trace_rec_t;
+
+void carma_pt_default_opts(carma_pt_opts_t* o);
+/* init: d values (SetStartingValue, src/carpack.cpp:233-265) or NULL (StartingValue draws).
+ * Host outputs: samples[n_ensembles][nsamples][d], logposts[n_ensembles][nsamples],
+ * accept_rates[n_ensembles][ntemps] (may be NULL), exchange_rates[n_ensembles][ntemps] (may be NULL).
+ * Trace outputs (NULL unless opts->record_trace): ram_trace/exch_trace[n_ensembles][iters][ntemps],
+ * proposals[n_ensembles][iters][ntemps][d], iters = burnin + nsamples*thin. */
+int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* opts,
+                 size_t n_ensembles, const double* init, double* samples, double* logposts, double* accept_rates,
+                 double* exchange_rates, carma_pt_trace_rec_t* ram_trace, carma_pt_trace_rec_t* exch_trace,
+                 double* proposals);
+/* Device-resident variant used by the benchmark: outputs stay in HBM, no sync. */
+int carma_pt_run_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior,
+                     const carma_pt_opts_t* opts, size_t n_ensembles, const double* d_init, double* d_samples,
+                     double* d_logposts, double* d_accept_rates, double* d_exchange_rates, void* stream);
+
+/* ---- utilities ---------------------------------------------------------------------------- */
+/* Saturating FP64 FMA micro-benchmark on `device`: returns sustained DFMA TFLOP/s (2 flops per
+ * FMA).  Used by bench.py as the measured FP64 roofline denominator. */
+int carma_fp64_peak_tflops(int device, double* tflops);
+/* Philox4x32-10 block and the Student-t draw built on it, exported so tests can pin the device
+ * RNG against the oracle bit for bit. */
+int carma_philox_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out4);
+int carma_tdist_dev(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, int dof, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARMA_B200_H */

@@ -1,0 +1,412 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via carma_pack_b200._lib) against the CPU
+oracle and the committed golden vectors produced by the reference's own numpy code.
+
+Tolerance (BASELINE.json north_star): log-densities within 1e-9 relative of the reference CPU
+filter; -inf / NaN must fall in the same class.  For parameter vectors where the reference
+algorithm itself is ill-conditioned (near-degenerate AR roots: its own double-precision result
+moves by more than the tolerance when re-evaluated in long double), the comparison is made against
+that intrinsic noise floor instead; such rows are counted and must stay rare.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_case_names
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def C():
+    import carma_pack_b200 as c
+    if c._lib.device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return c
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def to_prior(C, opr):
+    return C.Prior(opr.max_stdev, opr.max_freq, opr.min_freq, opr.kappa_low, opr.kappa_high, opr.measerr_dof)
+
+
+def assert_logpost_parity(got, want, want_ld=None, rtol=RTOL, max_illcond_frac=0.002, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    fin_w, fin_g = np.isfinite(want), np.isfinite(got)
+    # same class: finite / -inf / nan
+    assert np.array_equal(fin_w, fin_g), "%s: finite-class mismatch at %s" % (what, np.where(fin_w != fin_g)[0][:10])
+    ninf_w, ninf_g = want == -np.inf, got == -np.inf
+    assert np.array_equal(ninf_w, ninf_g), "%s: -inf class mismatch" % what
+    err = np.abs(got[fin_w] - want[fin_w])
+    tol = rtol * np.maximum(np.abs(want[fin_w]), 1.0)
+    bad = err > tol
+    if want_ld is None:
+        assert not bad.any(), "%s: max rel err %.3e" % (what, np.max(err / np.maximum(np.abs(want[fin_w]), 1.0)))
+        return 0
+    # rows where the reference algorithm itself is not reproducible to rtol in double precision
+    noise = np.abs(np.asarray(want_ld)[fin_w] - want[fin_w])
+    really_bad = bad & (err > 50.0 * noise + tol)
+    assert not really_bad.any(), "%s: %d rows differ beyond tolerance and beyond the oracle's own noise floor" % (
+        what, really_bad.sum())
+    assert bad.mean() <= max_illcond_frac, "%s: %.4f of rows needed the noise-floor criterion" % (what, bad.mean())
+    return int(bad.sum())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_filter_matches_golden_and_oracle(C, O, kelly):
+    s = C.Series(kelly["t"], kelly["y"], kelly["yerr"])
+    mean, var = s.filter(float(kelly["sigsqr"]), kelly["roots"], kelly["ma"])
+    assert mean[0] == 0.0
+    assert abs(var[0] - (2.3 ** 2 + kelly["yerr"][0] ** 2)) < 1e-10  # carma_unit_tests.cpp:441-444
+    np.testing.assert_allclose(mean, kelly["mean"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(var, kelly["var"], rtol=1e-9)
+    om, ov = O.filterp(kelly["t"], kelly["y"], kelly["yerr"], float(kelly["sigsqr"]), kelly["roots"], kelly["ma"])
+    np.testing.assert_allclose(mean, om, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(var, ov, rtol=1e-9)
+    y = kelly["y"]
+    ll = np.cumsum(-0.5 * np.log(var) - 0.5 * (y - mean) ** 2 / var)
+    assert abs(ll[269] - 7.828450879851) < 1e-8
+    assert abs(ll[999] - 49.705283285319) < 5e-8
+    # scaled / centred variant
+    m2, v2 = s.filter(float(kelly["sigsqr"]), kelly["roots"], kelly["ma"], measerr_scale=1.3, mu=0.25)
+    ll2 = np.sum(-0.5 * np.log(v2) - 0.5 * (y - 0.25 - m2) ** 2 / v2)
+    assert abs(ll2 - 41.593403983566) < 5e-8
+    s.close()
+
+
+def test_predict_matches_golden_and_oracle(C, O, kelly):
+    s = C.Series(kelly["t"], kelly["y"], kelly["yerr"])
+    s2, roots, ma = float(kelly["sigsqr"]), kelly["roots"], kelly["ma"]
+    qm, qv = s.predict(s2, roots, ma, kelly["predict_t"])
+    np.testing.assert_allclose(qm, kelly["predict_mean"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(qv, kelly["predict_var"], rtol=1e-8)
+    t = kelly["t"]
+    span = t[-1] - t[0]
+    tq = np.concatenate([[t[0] - 0.01 * span, t[0] - 1e-6, t[-1] + 0.05 * span, t[5], t[-1]],
+                         np.random.default_rng(0).uniform(t[0], t[-1], 40)])
+    qm, qv = s.predict(s2, roots, ma, tq)
+    om, ov = O.predictp(t, kelly["y"], kelly["yerr"], s2, roots, ma, tq)
+    np.testing.assert_allclose(qm, om, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(qv, ov, rtol=1e-8)
+    s.close()
+
+
+def test_kalmanfilter1_semantics(C, O, car1_cases):
+    """KalmanFilter1 == general filter with p=1, omega=(-w,0) (kfilter.cpp:19-48)."""
+    t, y, e = car1_cases["t"], car1_cases["y"], car1_cases["yerr"]
+    s = C.Series(t, y, e)
+    th = car1_cases["theta"][0]
+    w = np.exp(th[3])
+    mean, var = s.filter(2 * th[0] ** 2 * w, [-w + 0j], [1.0], measerr_scale=th[1], mu=th[2])
+    np.testing.assert_allclose(var, car1_cases["var"][0], rtol=1e-9)
+    np.testing.assert_allclose(mean, car1_cases["mean"][0], rtol=0, atol=1e-9)
+    tq = np.array([t[0] - 3.0, 0.5 * (t[3] + t[4]), t[-1] + 10.0])
+    qm, qv = s.predict(2 * th[0] ** 2 * w, [-w + 0j], [1.0], tq, measerr_scale=th[1], mu=th[2])
+    om, ov = O.predict1(t, y - th[2], np.sqrt(th[1]) * e, 2 * th[0] ** 2 * w, w, tq)
+    np.testing.assert_allclose(qm, om, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(qv, ov, rtol=1e-9)
+    s.close()
+
+
+def _series_for(cases, name):
+    if name == "c53":
+        return cases["t270"], cases["y270"], cases["ysig270"]
+    return cases["t60"], cases["y60"], cases["ysig60"]
+
+
+def test_loglik_golden_all_pq(C, O, loglik_cases):
+    """Every (p,q) family against the reference's numpy LogDensity (golden) and the oracle."""
+    for name in golden_case_names(loglik_cases):
+        p, q = int(loglik_cases[name + "_p"]), int(loglik_cases[name + "_q"])
+        t, y, e = _series_for(loglik_cases, name)
+        kind = C.KIND_CARMA if q > 0 else C.KIND_CARP
+        s = C.Series(t, y, e)
+        th = loglik_cases[name + "_theta"]
+        got = s.loglik(kind, p, q, th, flags=C.IGNORE_BOUNDS)
+        assert_logpost_parity(got, loglik_cases[name + "_logpost"], what="golden " + name)
+        assert_logpost_parity(got, O.logdensity(kind, p, q, t, y, e, th, ignore_prior=True), what="oracle " + name)
+        # LOGLIK_ONLY drops exactly the prior term
+        got_ll = s.loglik(kind, p, q, th, flags=C.IGNORE_BOUNDS | C.LOGLIK_ONLY)
+        np.testing.assert_allclose(got_ll, loglik_cases[name + "_loglik"], rtol=1e-9, atol=1e-9)
+        s.close()
+
+
+def test_loglik_zcarma_zcar_car1(C, O, loglik_cases, car1_cases):
+    t, y, e = loglik_cases["t60"], loglik_cases["y60"], loglik_cases["ysig60"]
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    opr = O.default_prior(t, y)
+    assert np.allclose(pr.as_tuple(), (opr.max_stdev, opr.max_freq, opr.min_freq, opr.kappa_low, opr.kappa_high,
+                                       opr.measerr_dof), rtol=1e-14)
+    got = s.loglik(C.KIND_ZCARMA, 5, 0, loglik_cases["z5_theta"], prior=pr, flags=C.IGNORE_BOUNDS)
+    assert_logpost_parity(got, loglik_cases["z5_logpost"], what="zcarma golden")
+    # ZCAR is evaluated as CAR(p) by the reference
+    a = s.loglik(C.KIND_ZCAR, 5, 0, loglik_cases["c50_theta"], flags=C.IGNORE_BOUNDS)
+    b = s.loglik(C.KIND_CARP, 5, 0, loglik_cases["c50_theta"], flags=C.IGNORE_BOUNDS)
+    assert np.array_equal(a, b)
+    s.close()
+    t, y, e = car1_cases["t"], car1_cases["y"], car1_cases["yerr"]
+    s = C.Series(t, y, e)
+    got = s.loglik(C.KIND_CAR1, 1, 0, car1_cases["theta"])
+    assert_logpost_parity(got, car1_cases["logpost"], what="car1 brute-force GP")
+    assert_logpost_parity(got, O.logdensity(O.KIND_CAR1, 1, 0, t, y, e, car1_cases["theta"]), what="car1 oracle")
+    s.close()
+
+
+def test_prior_bounds_give_minus_inf(C, loglik_cases):
+    """carma_unit_tests.cpp:1116-1265"""
+    t, y, e = loglik_cases["t270"], loglik_cases["y270"], loglik_cases["ysig270"]
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    th0 = loglik_cases["c53_theta"][0].copy()
+    rows = [th0.copy()]
+    th = th0.copy(); th[0] = pr.max_stdev * 1.01; rows.append(th)
+    th = th0.copy(); th[0] = -0.1; rows.append(th)
+    th = th0.copy(); th[1] = 0.49; rows.append(th)
+    th = th0.copy(); th[1] = 2.01; rows.append(th)
+    th = th0.copy(); th[4] = np.log(4 * np.pi * pr.max_freq * 1.5); th[3] = 2 * th[4]; rows.append(th)
+    th = th0.copy(); th[7] = np.log(2 * np.pi * pr.min_freq * 0.5); rows.append(th)
+    th = th0.copy(); th[3:5], th[5:7] = th0[5:7].copy(), th0[3:5].copy(); rows.append(th)
+    th = th0.copy(); th[5:7] = th[3:5]; rows.append(th)
+    got = s.loglik(C.KIND_CARMA, 5, 3, np.array(rows), prior=pr)
+    assert np.isfinite(got[0])
+    assert np.all(got[1:] == -np.inf)
+    got = s.loglik(C.KIND_CARMA, 5, 3, np.array(rows), prior=pr, flags=C.IGNORE_BOUNDS)
+    assert np.isfinite(got[3]) and np.isfinite(got[4])
+    s.close()
+
+
+def test_loglik_config2_65536_thetas(C, O):
+    """BASELINE config 2: 65,536 CARMA(5,3) parameter vectors on one ny=270 series, every row against the oracle."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(270, 270)
+    th = synth.theta_batch(65536, t, y, seed=2)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    got = s.loglik(C.KIND_CARMA, 5, 3, th, prior=pr)
+    opr = O.default_prior(t, y)
+    want = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr)
+    assert 0.5 < np.isfinite(want).mean() < 1.0  # both the filter path and the -inf early-out are exercised
+    want_ld = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr, long_double=True)
+    n_ill = assert_logpost_parity(got, want, want_ld, what="config2")
+    print("config2: %d of 65536 rows used the noise-floor criterion" % n_ill)
+    # idempotence / determinism: same input, same bits
+    got2 = s.loglik(C.KIND_CARMA, 5, 3, th, prior=pr)
+    assert np.array_equal(got, got2, equal_nan=True)
+    s.close()
+
+
+def test_loglik_long_series_chunked_pipeline(C, O, kelly):
+    """ny = 1000 and 5000 exercise the double-buffered TMA pipeline (chunks of 512 points)."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(5)
+    for ny in (1000, 5001):
+        t, y, e = synth.readme_series(ny, ny)
+        th = synth.theta_batch(256, t, y, seed=ny)
+        th[1] = th[0]  # duplicates must agree bitwise
+        s = C.Series(t, y, e)
+        got = s.loglik(C.KIND_CARMA, 5, 3, th)
+        want = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th)
+        want_ld = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, long_double=True)
+        assert_logpost_parity(got, want, want_ld, max_illcond_frac=0.02, what="ny=%d" % ny)
+        assert got[0] == got[1] or (np.isnan(got[0]) and np.isnan(got[1]))
+        s.close()
+    # kelly fixture through LogDensity-like path is covered by the golden filter test; here the
+    # time-shift invariance property at full length: only dt enters the filter
+    t, y, e = kelly["t"], kelly["y"], kelly["yerr"]
+    th = synth.prior_draws(64, 4, 2, t, y, rng)
+    s1, s2 = C.Series(t, y, e), C.Series(t + 1000.0, y, e)
+    a = s1.loglik(C.KIND_CARMA, 4, 2, th, flags=C.IGNORE_BOUNDS)
+    b = s2.loglik(C.KIND_CARMA, 4, 2, th, flags=C.IGNORE_BOUNDS)
+    np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-8, equal_nan=True)
+    s1.close(); s2.close()
+
+
+def test_scaling_property(C):
+    """Size-independent property: (y, yerr, sigma_y, mu) -> c * (...) shifts the log-likelihood by -ny log c."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(270, 11)
+    th = synth.theta_batch(512, t, y, seed=4)
+    c = 3.7
+    th2 = th.copy(); th2[:, 0] *= c; th2[:, 2] *= c
+    s1, s2 = C.Series(t, y, e), C.Series(t, c * y, c * e)
+    a = s1.loglik(C.KIND_CARMA, 5, 3, th, flags=C.IGNORE_BOUNDS | C.LOGLIK_ONLY)
+    b = s2.loglik(C.KIND_CARMA, 5, 3, th2, flags=C.IGNORE_BOUNDS | C.LOGLIK_ONLY)
+    fin = np.isfinite(a) & np.isfinite(b)
+    assert fin.mean() > 0.9
+    np.testing.assert_allclose(b[fin], a[fin] - 270 * np.log(c), rtol=1e-8, atol=1e-6)
+    s1.close(); s2.close()
+
+
+def test_multi_series_ragged(C, O):
+    """K4: ragged batch, one theta per curve, per-curve priors."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(9)
+    ar, ma, s2 = synth.carma31_truth()
+    ts, ys, es, off, thetas = [], [], [], [0], []
+    ncurves = 300
+    for c in range(ncurves):
+        ny = int(rng.integers(20, 140)) if c else 2  # include the minimum length
+        t = synth.cauchy_times(ny, rng)
+        y0 = 5.0 + synth.carma_process(t, s2, ar, ma, rng)
+        e = np.full(ny, 0.1) * rng.uniform(0.5, 2.0, ny)
+        y = y0 + e * rng.standard_normal(ny)
+        ts.append(t); ys.append(y); es.append(e); off.append(off[-1] + ny)
+        thetas.append(synth.prior_draws(1, 3, 1, t, y, rng)[0] if ny > 4 else np.array([1.0, 1.0, 5.0, -1.0, -0.5, -3.0, 0.5]))
+    t, y, e = np.concatenate(ts), np.concatenate(ys), np.concatenate(es)
+    th = np.array(thetas)
+    m = C.MultiSeries(t, y, e, off)
+    pri = m.default_priors()
+    got = m.loglik(C.KIND_CARMA, 3, 1, th)
+    opri = [O.default_prior(ts[c], ys[c]) for c in range(ncurves)]
+    for c in (0, 1, 17):
+        assert np.allclose(tuple(pri[c]), (opri[c].max_stdev, opri[c].max_freq, opri[c].min_freq, opri[c].kappa_low,
+                                           opri[c].kappa_high, 50.0), rtol=1e-13)
+    want = O.logdensity_multi(O.KIND_CARMA, 3, 1, t, y, e, off, th, opri)
+    assert_logpost_parity(got, want, what="multi")
+    got2 = m.loglik(C.KIND_CARMA, 3, 1, th, flags=C.IGNORE_BOUNDS)
+    want2 = O.logdensity_multi(O.KIND_CARMA, 3, 1, t, y, e, off, th, opri, ignore_prior=True)
+    assert_logpost_parity(got2, want2, rtol=1e-8, what="multi ignore-bounds")
+    m.close()
+
+
+def test_philox_bit_exact_and_tdist(C, O):
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        c = [int(x) for x in rng.integers(0, 2 ** 32, 4)]
+        seed = int(rng.integers(0, 2 ** 63))
+        assert C._lib.philox_dev(c[0], c[1], c[2], c[3], seed) == O.philox(c[0], c[1], c[2], c[3], seed)
+    # Random123 known-answer vector for Philox4x32-10: counter = key = 0
+    assert O.philox(0, 0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert C._lib.philox_dev(0, 0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    for j in range(30):
+        a = C._lib.tdist_dev(77, 5, j, j % 11, 8)
+        b = O.tdist(77, 5, j, j % 11, 8)
+        assert abs(a - b) <= 1e-13 * max(1.0, abs(b))
+
+
+# ------------------------------------------------------------------------------------------------
+# PT-MCMC
+# ------------------------------------------------------------------------------------------------
+def _check_trace_against_oracle(C, O, res, kind, p, q, t, y, e, opr, ntemps, tmax=100.0):
+    """Record/replay: every proposal's log-density, and every accept / exchange decision, re-derived
+    on the CPU from the recorded state."""
+    temps = np.exp(np.linspace(0.0, np.log(tmax), ntemps)) if ntemps > 1 else np.ones(1)
+    rt, xt, prop = res["ram_trace"][0], res["exchange_trace"][0], res["proposals"][0]
+    iters = rt.shape[0]
+    d = prop.shape[-1]
+    lp_o = O.logdensity(kind, p, q, t, y, e, prop.reshape(-1, d), prior=opr).reshape(iters, ntemps)
+    lp_ld = O.logdensity(kind, p, q, t, y, e, prop.reshape(-1, d), prior=opr, long_double=True).reshape(iters, ntemps)
+    assert_logpost_parity(rt["lp_prop"].ravel(), lp_o.ravel(), lp_ld.ravel(), max_illcond_frac=0.01, what="pt proposals")
+    nflip = 0
+    for it in range(iters):
+        for c in range(ntemps):
+            r = rt[it, c]
+            a = (lp_o[it, c] - r["lp_cur"]) / temps[c]
+            if not np.isfinite(a):
+                assert r["accepted"] == 0 and r["alpha"] == 0.0
+                continue
+            alpha = min(np.exp(a), 1.0)
+            assert abs(alpha - r["alpha"]) <= 1e-7 * max(alpha, 1e-30) + 1e-300
+            want_acc = r["u"] < alpha
+            if want_acc != bool(r["accepted"]):
+                # only allowed when u sits within the tolerance band of alpha
+                assert abs(r["u"] - alpha) <= 1e-7 * alpha
+                nflip += 1
+            if c > 0:
+                x = xt[it, c]
+                ax = (x["lp_prop"] - x["lp_cur"]) / temps[c] + (x["lp_cur"] - x["lp_prop"]) / temps[c - 1]
+                ax = min(np.exp(ax), 1.0)
+                if not np.isfinite(ax):
+                    ax = 0.0
+                assert abs(ax - x["alpha"]) <= 1e-12 * max(ax, 1e-30) + 1e-300
+                assert bool(x["accepted"]) == (x["u"] < x["alpha"])
+    return nflip
+
+
+@pytest.mark.parametrize("kind_name,p,q,ntemps", [("CARMA", 5, 3, 10), ("CARP", 3, 0, 4), ("CAR1", 1, 0, 1),
+                                                  ("ZCARMA", 4, 0, 3)])
+def test_pt_run_record_replay_and_trajectory(C, O, kind_name, p, q, ntemps):
+    from carma_pack_b200 import synth
+    kind = getattr(C, "KIND_" + kind_name)
+    t, y, e = synth.readme_series(120, 42)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    opr = O.default_prior(t, y)
+    nsamples, burnin, thin = 60, 80, 2
+    res = s.pt_run(kind, p, q, nsamples, burnin, thin=thin, ntemps=ntemps, n_ensembles=3, seed=1234, prior=pr,
+                   record_trace=True)
+    assert np.all(np.isfinite(res["logposts"]))
+    # stored log-posteriors equal a fresh LogDensity of the stored samples (carma_unit_tests.cpp:1068-1113, 1e-8 rel)
+    d = res["samples"].shape[-1]
+    relp = s.loglik(kind, p, q, res["samples"].reshape(-1, d), prior=pr).reshape(res["logposts"].shape)
+    np.testing.assert_allclose(relp, res["logposts"], rtol=1e-8)
+    nflip = _check_trace_against_oracle(C, O, res, kind, p, q, t, y, e, opr, ntemps)
+    assert nflip == 0
+    # identical Philox streams => the oracle's sequential-order sampler follows the same trajectory
+    ores = O.pt_run(kind, p, q, t, y, e, nsamples, burnin, thin=thin, ntemps=ntemps, seed=1234, ensemble=0, prior=opr,
+                    want_trace=True)
+    acc_g = res["ram_trace"][0]["accepted"]
+    acc_o = ores["ram_trace"]["accepted"]
+    x_g = res["exchange_trace"][0]["accepted"][:, 1:]
+    x_o = ores["exchange_trace"]["accepted"][:, 1:]
+    assert np.array_equal(acc_g, acc_o), "accept decisions diverged at iteration %d" % np.argmax((acc_g != acc_o).any(axis=1))
+    assert np.array_equal(x_g, x_o)
+    np.testing.assert_allclose(res["proposals"][0], ores["proposals"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(res["samples"][0], ores["samples"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(res["logposts"][0], ores["logposts"], rtol=1e-8)
+    np.testing.assert_allclose(res["accept_rates"][0], ores["accept_rates"], atol=1e-12)
+    # ensemble 1 of the same launch == a separate launch with ensemble_offset=1
+    res1 = s.pt_run(kind, p, q, nsamples, burnin, thin=thin, ntemps=ntemps, n_ensembles=1, seed=1234,
+                    ensemble_offset=1, prior=pr)
+    assert np.array_equal(res1["samples"][0], res["samples"][1])
+    s.close()
+
+
+def test_pt_run_with_init_and_parallel_mode(C, O):
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(90, 7)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    init = synth.readme_theta(3)
+    res = s.pt_run(C.KIND_CARMA, 5, 3, 40, 40, ntemps=5, n_ensembles=2, seed=9, init=init, prior=pr, record_trace=True)
+    ores = O.pt_run(O.KIND_CARMA, 5, 3, t, y, e, 40, 40, ntemps=5, seed=9, init=init, prior=O.default_prior(t, y),
+                    want_trace=True)
+    # first proposals start from init for every chain
+    assert np.array_equal(res["ram_trace"][0]["accepted"], ores["ram_trace"]["accepted"])
+    np.testing.assert_allclose(res["samples"][0], ores["samples"], rtol=1e-7, atol=1e-9)
+    # order_mode 1 (concurrent proposals) is a valid sampler: finite, and consistent stored log-posteriors
+    r1 = s.pt_run(C.KIND_CARMA, 5, 3, 50, 50, ntemps=5, n_ensembles=4, seed=9, prior=pr, order_mode=1)
+    relp = s.loglik(C.KIND_CARMA, 5, 3, r1["samples"].reshape(-1, 11), prior=pr).reshape(r1["logposts"].shape)
+    np.testing.assert_allclose(relp, r1["logposts"], rtol=1e-8)
+    s.close()
+
+
+def test_pt_posterior_recovers_truth_car1(C):
+    """Statistical check in the spirit of carma_unit_tests.cpp:1319-1375 (posterior within 3 sigma of truth),
+    using many independent ensembles instead of one long chain."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(3)
+    tau, sig_y, mu = 25.0, 1.5, 3.0
+    t = np.cumsum(rng.uniform(0.5, 1.5, 300))
+    y0 = mu + synth.car1_process(t, 2 * sig_y ** 2 / tau, tau, rng)
+    e = np.full(t.size, 0.15)
+    y = y0 + e * rng.standard_normal(t.size)
+    s = C.Series(t, y, e)
+    res = s.pt_run(C.KIND_CAR1, 1, 0, 400, 1500, thin=5, ntemps=1, n_ensembles=64, seed=5)
+    smp = res["samples"].reshape(-1, 4)
+    assert 0.1 < res["accept_rates"].mean() < 0.5  # RAM targets 0.25
+    logw = smp[:, 3]
+    assert abs(logw.mean() - np.log(1 / tau)) < 3 * logw.std()
+    assert abs(smp[:, 2].mean() - mu) < 3 * smp[:, 2].std()
+    assert abs(smp[:, 0].mean() - sig_y) < 3 * smp[:, 0].std()
+    assert abs(smp[:, 1].mean() - 1.0) < 3 * smp[:, 1].std()
+    # between-ensemble agreement (independent chains sample the same posterior)
+    ens_means = res["samples"][:, :, 3].mean(axis=1)
+    assert ens_means.std() < 3 * logw.std()
+    s.close()
