@@ -37,20 +37,46 @@ struct KalmanCplx {
     __device__ bool reset(double sigsqr, const double* omega_reim, const double* ma, int p_, double e2_0, double y0) {
         p = p_;
         for (int k = 0; k < p; k++) w[k] = cx(omega_reim[2 * k], omega_reim[2 * k + 1]);
-        bool singular = false;
-        cxd J[MAX_P];
         for (int k = 0; k < p; k++) {
-            cxd dp = cx(1, 0);
-            for (int l = 0; l < p; l++)
-                if (l != k) dp = dp * (w[k] - w[l]);
-            if (dp.re == 0.0 && dp.im == 0.0) singular = true;
-            J[k] = cdiv(cx(1, 0), dp);
             cxd s = cx(ma[p - 1], 0);
             for (int l = p - 2; l >= 0; l--) s = s * w[k] + cx(ma[l], 0);
             b[k] = s;
             x[k] = cx(0, 0);
         }
-        if (singular) return false;
+        // J = E^{-1} e_p by LU with partial pivoting (arma::solve -> zgesv, kfilter.cpp:152-158)
+        cxd J[MAX_P];
+        {
+            cxd A[MAX_P][MAX_P];
+            for (int k = 0; k < p; k++) {
+                cxd pw = cx(1, 0);
+                A[0][k] = pw;
+                for (int i = 1; i < p; i++) { pw = pw * w[k]; A[i][k] = pw; }
+                J[k] = cx(k == p - 1 ? 1.0 : 0.0, 0.0);
+            }
+            for (int k = 0; k < p; k++) {
+                int piv = k;
+                double best = fabs(A[k][k].re) + fabs(A[k][k].im);
+                for (int i = k + 1; i < p; i++) {
+                    double v = fabs(A[i][k].re) + fabs(A[i][k].im);
+                    if (v > best) { best = v; piv = i; }
+                }
+                if (!(best > 0.0) || !isfinite(best)) return false;
+                if (piv != k) {
+                    for (int j = 0; j < p; j++) { cxd tmp = A[k][j]; A[k][j] = A[piv][j]; A[piv][j] = tmp; }
+                    cxd tr = J[k]; J[k] = J[piv]; J[piv] = tr;
+                }
+                for (int i = k + 1; i < p; i++) {
+                    cxd l = cdiv(A[i][k], A[k][k]);
+                    for (int j = k + 1; j < p; j++) A[i][j] = A[i][j] - l * A[k][j];
+                    J[i] = J[i] - l * J[k];
+                }
+            }
+            for (int i = p - 1; i >= 0; i--) {
+                cxd s = J[i];
+                for (int j = i + 1; j < p; j++) s = s - A[i][j] * J[j];
+                J[i] = cdiv(s, A[i][i]);
+            }
+        }
         for (int i = 0; i < p; i++)
             for (int j = i; j < p; j++) {
                 cxd v = cdiv((-sigsqr) * (J[i] * conj(J[j])), w[i] + conj(w[j]));

@@ -83,10 +83,67 @@ __device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cx
     return cmask;
 }
 
-// Returns TT_NEG_INF when the log-density is -inf (bounds violated / singular), else TT_OK.
+// Solve E J = e_{P-1} with E(i,k) = w_k^i (kfilter.cpp:144-158) by LU with partial pivoting
+// (pivot = max |re|+|im|, as LAPACK izamax).  Fully unrolled, row swaps predicated, so everything
+// stays in registers.  Returns false on an exactly singular system.
 template <int P>
-__device__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
-                               RealParams<P>& out) {
+__device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
+    cxd A[P][P];
+    cxd rhs[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        cxd pw = cx(1, 0);
+        A[0][k] = pw;
+#pragma unroll
+        for (int i = 1; i < P; i++) {
+            pw = pw * w[k];
+            A[i][k] = pw;
+        }
+        rhs[k] = cx(k == P - 1 ? 1.0 : 0.0, 0.0);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        int piv = k;
+        double best = fabs(A[k][k].re) + fabs(A[k][k].im);
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {
+            double v = fabs(A[i][k].re) + fabs(A[i][k].im);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (!(best > 0.0) || !isfinite(best)) ok = false;
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {
+            if (i == piv) {
+#pragma unroll
+                for (int j = k; j < P; j++) { cxd tmp = A[k][j]; A[k][j] = A[i][j]; A[i][j] = tmp; }
+                cxd tr = rhs[k]; rhs[k] = rhs[i]; rhs[i] = tr;
+            }
+        }
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {
+            cxd l = cdiv(A[i][k], A[k][k]);
+#pragma unroll
+            for (int j = k + 1; j < P; j++) A[i][j] = A[i][j] - l * A[k][j];
+            rhs[i] = rhs[i] - l * rhs[k];
+        }
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; i--) {
+        cxd s = rhs[i];
+#pragma unroll
+        for (int j = i + 1; j < P; j++) s = s - A[i][j] * J[j];
+        J[i] = cdiv(s, A[i][i]);
+    }
+    return ok;
+}
+
+// Returns TT_NEG_INF when the log-density is -inf (bounds violated / singular), else TT_OK.
+// __noinline__: the prologue (LU on a PxP complex matrix) gets its own register allocation, so it
+// cannot push spills into the time loop of the calling kernel.
+template <int P>
+__device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
+                                            RealParams<P>& out) {
     constexpr double PI = 3.14159265358979323846;
     const double ysigma = th[0], scale = th[1];
     out.scale = scale;
@@ -186,19 +243,13 @@ __device__ int transform_theta(int kind, int q, unsigned flags, const carma_prio
     else
         sigsqr = ysigma * ysigma / var_acc.re;  // carpack.hpp:316-319, 391-395
 
-    // ---- J = E^{-1} e_p for the Vandermonde E (kfilter.cpp:144-158), closed form
+    // ---- J = E^{-1} e_p for the Vandermonde E (kfilter.cpp:144-158): LU with partial pivoting, as
+    // arma::solve -> zgesv does.  (The closed form J_k = 1/prod_{l!=k}(w_k - w_l) has a smaller forward
+    // error per element but is NOT what the reference computes: the LU solution is backward stable,
+    // i.e. exact for slightly perturbed roots, and the massive cancellation in b V b^H for clustered
+    // roots is benign under such consistent perturbations while it amplifies independent ones.)
     cxd J[P];
-    bool singular = false;
-#pragma unroll
-    for (int k = 0; k < P; k++) {
-        cxd dp = cx(1, 0);
-#pragma unroll
-        for (int l = 0; l < P; l++)
-            if (l != k) dp = dp * (w[k] - w[l]);
-        if (dp.re == 0.0 && dp.im == 0.0) singular = true;
-        J[k] = cdiv(cx(1, 0), dp);
-    }
-    if (singular) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
+    if (!vandermonde_solve_last<P>(w, J)) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
 
     // ---- stationary covariance V (kfilter.cpp:165-172), h = V b^H, v0 = Re(b V b^H)
     cxd h[P];
@@ -227,8 +278,12 @@ __device__ int transform_theta(int kind, int q, unsigned flags, const carma_prio
             out.lam[2 * s + 1] = w[2 * s].im;
             out.c[2 * s] = 2.0 * b[2 * s].re;
             out.c[2 * s + 1] = -2.0 * b[2 * s].im;
-            out.h[2 * s] = h[2 * s].re;
-            out.h[2 * s + 1] = h[2 * s].im;
+            // h restricted to the conjugate-symmetric subspace: (h_{2s} + conj(h_{2s+1})) / 2.  The LU
+            // solution J is not exactly conjugate-symmetric (its error is cond(E) eps, consistent across
+            // components); averaging keeps c.h == Re(b V b^H) to rounding, which is what the reference's
+            // full complex recursion sees to first order in that asymmetry.
+            out.h[2 * s] = 0.5 * (h[2 * s].re + h[2 * s + 1].re);
+            out.h[2 * s + 1] = 0.5 * (h[2 * s].im - h[2 * s + 1].im);
         } else {
             out.lam[2 * s] = w[2 * s].re;
             out.lam[2 * s + 1] = w[2 * s + 1].re;
