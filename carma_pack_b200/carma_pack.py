@@ -1,0 +1,449 @@
+"""User-level Python API with the names and semantics of the reference's `carmcmc` package
+(src/carmcmc/carma_pack.py, src/carmcmc/__init__.py:1-4), driving the GPU path.
+
+    CarmaModel(time, y, ysig, p, q).run_mcmc(n) / .get_mle(p, q) / .choose_order(pmax)
+    CarmaSample, Car1Sample: posterior container with derived quantities, predict / simulate
+    get_ar_roots, power_spectrum, carma_variance, carma_process, car1_process
+
+Out of scope: matplotlib plots and summaries.  What differs on
+purpose from the reference:
+  * `get_mle` / `choose_order` run all random starts of a (p,q) model in lock-step: the starting
+    values come from short on-device MCMC runs (reference: carma_pack.py:199-216, one C++ MCMC run per
+    trial) and the L-BFGS-B fits of the reference (carma_pack.py:250, finite-difference gradient) are
+    replaced by a batched projected L-BFGS whose function and finite-difference gradient evaluations
+    are single batched GPU launches;
+  * CarmaSample computes `loglik` with one batched launch instead of one FFI call per stored
+    sample (carma_pack.py:307-313);
+  * Python-3 bugs of the reference are not reproduced.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import (KIND_CAR1, KIND_CARP, KIND_CARMA, KIND_ZCAR, KIND_ZCARMA, IGNORE_BOUNDS, Series, model_dim)
+from .synth import get_ar_roots, power_spectrum, carma_variance, carma_process, car1_process  # noqa: F401
+
+
+def _kind_for(p, q):
+    if p == 1:
+        return KIND_CAR1
+    return KIND_CARMA if q > 0 else KIND_CARP
+
+
+class OptimizeResult(dict):
+    """Minimal stand-in for scipy.optimize.OptimizeResult (attributes x, fun, message, success, nit, nfev)."""
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+
+
+def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
+    """Minimise fun over a box for every row of x0 simultaneously.
+
+    fun_batch maps an (n, d) array to n function values (non-finite values are treated as +inf).
+    Projected L-BFGS with forward-difference gradients and Armijo backtracking; all rows advance in
+    lock-step so that each iteration costs a few batched evaluations (n*(d+1) rows for the gradient).
+    """
+    x = np.clip(np.array(x0, dtype=float), lower, upper)
+    n, d = x.shape
+    big = 1e300
+
+    def f_safe(z):
+        v = np.asarray(fun_batch(z), dtype=float)
+        return np.where(np.isfinite(v), v, big)
+
+    def grad(z, fz):
+        # forward differences, stepping inward at the upper bound (scipy approx_fprime epsilon = 1e-8)
+        h = np.full((n, d), fd_eps)
+        h = np.where(z + h > upper, -h, h)
+        zz = np.repeat(z[:, None, :], d, axis=1)
+        idx = np.arange(d)
+        zz[:, idx, idx] += h
+        fv = f_safe(zz.reshape(n * d, d)).reshape(n, d)
+        g = (fv - fz[:, None]) / h
+        return np.where(np.abs(fv) >= big, 0.0, g)
+
+    f = f_safe(x)
+    g = grad(x, f)
+    S, Y = [], []
+    active = f < big
+    nfev = n * (d + 1)
+    nit = 0
+    for nit in range(1, maxiter + 1):
+        # projected gradient: zero the components pushing against an active bound
+        at_lo = (x <= lower) & (g > 0)
+        at_hi = (x >= upper) & (g < 0)
+        pg = np.where(at_lo | at_hi, 0.0, g)
+        conv = np.max(np.abs(pg), axis=1) < gtol
+        active &= ~conv
+        if not active.any():
+            break
+        # two-loop recursion, vectorised over rows
+        qv = pg.copy()
+        alphas = []
+        for s, yv in zip(reversed(S), reversed(Y)):
+            rho = 1.0 / np.maximum(np.sum(s * yv, axis=1), 1e-300)
+            a = rho * np.sum(s * qv, axis=1)
+            qv -= a[:, None] * yv
+            alphas.append((a, rho))
+        if S:
+            gam = np.sum(S[-1] * Y[-1], axis=1) / np.maximum(np.sum(Y[-1] * Y[-1], axis=1), 1e-300)
+            qv *= np.clip(gam, 1e-8, 1e8)[:, None]
+        else:
+            qv *= (1.0 / np.maximum(np.linalg.norm(pg, axis=1), 1.0))[:, None]
+        for (a, rho), s, yv in zip(reversed(alphas), S, Y):
+            b = rho * np.sum(yv * qv, axis=1)
+            qv += (a - b)[:, None] * s
+        direction = -np.where(at_lo | at_hi, 0.0, qv)
+        slope = np.sum(direction * pg, axis=1)
+        bad = ~(slope < 0)
+        direction[bad] = -pg[bad]
+        slope[bad] = -np.sum(pg[bad] ** 2, axis=1)
+        # batched Armijo backtracking on the projected path
+        t = np.ones(n)
+        xn, fn = x.copy(), f.copy()
+        todo = active.copy()
+        for _ in range(25):
+            if not todo.any():
+                break
+            cand = np.clip(x + t[:, None] * direction, lower, upper)
+            fc = f_safe(cand)
+            nfev += n
+            ok = todo & (fc <= f + 1e-4 * t * slope)
+            xn[ok], fn[ok] = cand[ok], fc[ok]
+            todo &= ~ok
+            t[todo] *= 0.5
+        moved = active & ~todo
+        small = moved & ((f - fn) <= ftol * np.maximum(np.maximum(np.abs(f), np.abs(fn)), 1.0))
+        gn = g.copy()
+        if moved.any():
+            gnew = grad(xn, fn)
+            nfev += n * d
+            gn[moved] = gnew[moved]
+        s = np.where(moved[:, None], xn - x, 0.0)
+        yv = np.where(moved[:, None], gn - g, 0.0)
+        curv = np.sum(s * yv, axis=1) > 1e-12
+        if curv.any():
+            S.append(np.where(curv[:, None], s, 0.0))
+            Y.append(np.where(curv[:, None], yv, 0.0))
+            if len(S) > m:
+                S.pop(0)
+                Y.pop(0)
+        x, f, g = xn, fn, gn
+        active &= ~todo   # line search failed: stop that row
+        active &= ~small
+    return x, f, nit, nfev
+
+
+class CarmaModel(object):
+    """Statistical inference assuming a CARMA(p,q) model (carma_pack.py:12-192)."""
+
+    def __init__(self, time, y, ysig, p=1, q=0, device=0):
+        if not p > q:
+            raise ValueError("Order of AR polynomial, p, must be larger than order of MA polynomial, q.")
+        time, y, ysig = np.asarray(time, float), np.asarray(y, float), np.asarray(ysig, float)
+        # unique, ascending times (carma_pack.py:32-35)
+        s_idx = np.argsort(time)
+        _, u_idx = np.unique(time[s_idx], return_index=True)
+        u_idx = s_idx[u_idx]
+        self.time, self.y, self.ysig = time[u_idx], y[u_idx], ysig[u_idx]
+        self.p, self.q = p, q
+        self.device = device
+        self.mcmc_sample = None
+        self._series = None
+
+    @property
+    def series(self):
+        if self._series is None:
+            self._series = Series(self.time, self.y, self.ysig, device=self.device)
+        return self._series
+
+    def run_mcmc(self, nsamples, nburnin=None, ntemperatures=None, nthin=1, init=None, seed=None, n_ensembles=1):
+        """Run the parallel-tempering RAM sampler on the GPU (carma_pack.py:53-90).
+
+        n_ensembles > 1 runs that many independent ensembles in the same launch and concatenates
+        their coolest chains (extension; the reference runs one)."""
+        p, q = self.p, self.q
+        if ntemperatures is None:
+            ntemperatures = max(10, p + q)
+        if nburnin is None:
+            nburnin = nsamples // 2
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+        kind = _kind_for(p, q)
+        if p == 1:
+            ntemperatures = 1  # run_mcmc_car1 has a single chain (carmcmc.cpp:30-77)
+        prior = self.series.default_prior(population_var=True)  # carmcmc.cpp:85-89
+        res = self.series.pt_run(kind, p, q, int(nsamples), int(nburnin), thin=int(nthin), ntemps=int(ntemperatures),
+                                 n_ensembles=int(n_ensembles), seed=seed, init=init, prior=prior)
+        d = model_dim(kind, p, q)
+        trace = res["samples"].reshape(-1, d)
+        logpost = res["logposts"].reshape(-1)
+        if p == 1:
+            sample = Car1Sample(self.time, self.y, self.ysig, trace=trace, logpost=logpost, series=self.series, prior=prior)
+        else:
+            sample = CarmaSample(self.time, self.y, self.ysig, trace=trace, logpost=logpost, p=p, q=q,
+                                 series=self.series, prior=prior)
+        sample.accept_rates = res["accept_rates"]
+        sample.exchange_rates = res["exchange_rates"]
+        self.mcmc_sample = sample
+        return sample
+
+    def _mle_bounds(self, p, q):
+        """Box bounds of the optimiser (carma_pack.py:218-240)."""
+        ysigma = self.y.std()
+        dt = np.diff(self.time)
+        max_freq = 0.9 / dt.min()
+        min_freq = 1.0 / (self.time.max() - self.time.min())
+        lo = [ysigma / 10.0, 0.9, -np.inf]
+        hi = [10.0 * ysigma, 1.1, np.inf]
+        if p == 1:
+            lo.append(np.log(min_freq)); hi.append(np.log(max_freq))
+        else:
+            lo += [np.log(min(min_freq ** 2, 2.0 * min_freq))] * p
+            hi += [np.log(max(max_freq ** 2, 2.0 * max_freq))] * p
+            lo += [-np.inf] * q
+            hi += [np.inf] * q
+        return np.array(lo), np.array(hi)
+
+    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200):
+        """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
+        in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored."""
+        kind = _kind_for(p, q)
+        d = model_dim(kind, p, q)
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+        prior = self.series.default_prior(population_var=True)
+        # initial guesses: nsamples=1, nburnin=25, nwalkers=10 MCMC runs (carma_pack.py:197-216)
+        res = self.series.pt_run(kind, p, q, 1, 25, ntemps=1 if p == 1 else 10, n_ensembles=ntrials, seed=seed,
+                                 prior=prior)
+        x0 = res["samples"][:, 0, :].copy()
+        x0[:, 1] = 1.0  # carma_pack.py:216
+        lo, hi = self._mle_bounds(p, q)
+        rng = np.random.default_rng(seed)
+        for j in range(d):  # carma_pack.py:244-248
+            if np.isfinite(lo[j]):
+                out = (x0[:, j] < lo[j]) | (x0[:, j] > hi[j])
+                x0[out, j] = rng.uniform(lo[j], hi[j], out.sum())
+        flags = 0 if p == 1 else IGNORE_BOUNDS  # SetMLE(True) only for p > 1 (carma_pack.py:242)
+
+        def negloglik(th):
+            return -self.series.loglik(kind, p, q, th, prior=prior, flags=flags)  # _carma_loglik, carma_pack.py:255-260
+
+        x, f, nit, nfev = batched_lbfgs(negloglik, x0, lo, hi, maxiter=maxiter)
+        best = int(np.argmin(f))
+        mle = OptimizeResult(x=x[best], fun=float(f[best]), nit=nit, nfev=nfev, success=bool(np.isfinite(f[best])),
+                             message="batched projected L-BFGS, best of %d starts" % ntrials,
+                             all_x=x, all_fun=f)
+        return mle
+
+    def choose_order(self, pmax, qmax=None, pqlist=None, njobs=1, ntrials=100, seed=None, verbose=True):
+        """Choose (p,q) by minimising AICc over a grid of MLEs (carma_pack.py:131-192)."""
+        if not pmax > 0:
+            raise ValueError("Order of AR polynomial must be at least 1.")
+        if qmax is None:
+            qmax = pmax - 1
+        if not pmax > qmax:
+            raise ValueError("Order of AR polynomial, p, must be larger than order of MA polynimial, q.")
+        if pqlist is None:
+            pqlist = [(p, q) for p in range(1, pmax + 1) for q in range(min(p, qmax + 1))]
+        MLEs = []
+        for k, (p, q) in enumerate(pqlist):
+            MLEs.append(self.get_mle(p, q, ntrials=ntrials, njobs=njobs, seed=None if seed is None else seed + k))
+        best_AICc, AICc, best_MLE = 1e300, [], MLEs[0]
+        if verbose:
+            print("p, q, AICc:")
+        for MLE, (p, q) in zip(MLEs, pqlist):
+            nparams = 2 + p + q  # sic, carma_pack.py:178
+            this_AICc = 2.0 * nparams + 2.0 * MLE.fun + 2.0 * nparams * (nparams + 1.0) / (self.time.size - nparams - 1.0)
+            if verbose:
+                print(p, q, this_AICc)
+            AICc.append(this_AICc)
+            if this_AICc < best_AICc:
+                best_MLE, best_AICc = MLE, this_AICc
+                self.p, self.q = p, q
+        if verbose:
+            print("Model with best AICc has p =", self.p, " and q = ", self.q)
+        return best_MLE, pqlist, AICc
+
+
+class MCMCSample(object):
+    """Dictionary of traces (subset of src/carmcmc/samplers.py:13-408 without the plots)."""
+
+    def __init__(self, trace=None, logpost=None):
+        self._samples = {}
+        if logpost is not None:
+            self._samples["logpost"] = np.asarray(logpost)
+        self.parameters = []
+
+    def get_samples(self, name):
+        return self._samples[name].copy()
+
+    def newaxis(self):
+        for k, v in self._samples.items():
+            if v.ndim == 1:
+                self._samples[k] = v[:, np.newaxis]
+
+    def effective_samples(self, name):
+        """Integrated-autocorrelation estimate of the effective sample size (samplers.py uses `acor`)."""
+        x = np.atleast_2d(self._samples[name].T)
+        out = []
+        for row in x:
+            r = row - row.mean()
+            n = r.size
+            ac = np.correlate(r, r, mode="full")[n - 1:] / max(np.dot(r, r), 1e-300)
+            tau, k = 1.0, 1
+            while k < n and ac[k] > 0.05:
+                tau += 2.0 * ac[k]
+                k += 1
+            out.append(n / tau)
+        return np.array(out)
+
+
+class CarmaSample(MCMCSample):
+    """MCMC samples of a CARMA(p,q) model with derived quantities (carma_pack.py:263-546)."""
+
+    def __init__(self, time, y, ysig, trace, logpost, p, q=0, series=None, prior=None, MLE=None):
+        super(CarmaSample, self).__init__(trace=trace, logpost=logpost)
+        self.time, self.y, self.ysig = time, y, ysig
+        self.p, self.q = p, q
+        self._series = series if series is not None else Series(time, y, ysig)
+        self._prior = prior if prior is not None else self._series.default_prior(True)
+        trace = np.asarray(trace)
+        # column names as samplers.py / carma_pack.py:286-305
+        self._samples["var"] = trace[:, 0] ** 2
+        self._samples["measerr_scale"] = trace[:, 1]
+        self._samples["mu"] = trace[:, 2]
+        self._samples["quad_coefs"] = np.exp(trace[:, 3:3 + p])
+        self._trace = trace
+        self._ar_roots()
+        self._ar_coefs()
+        self._ma_coefs(trace)
+        self._sigma_noise()
+        # loglik = LogDensity with SetMLE(True): one batched launch (carma_pack.py:307-313)
+        kind = KIND_CARMA if q > 0 else KIND_CARP
+        self._samples["loglik"] = self._series.loglik(kind, p, q, trace, prior=self._prior, flags=IGNORE_BOUNDS)
+        self.parameters = list(self._samples.keys())
+        self.newaxis()
+        self.mle = {}
+        if MLE is not None:
+            self.add_mle(MLE)
+
+    def _ar_roots(self):  # carma_pack.py:439-467
+        qc = self._samples["quad_coefs"]
+        n, p = qc.shape[0], self.p
+        roots = np.empty((n, p), dtype=complex)
+        for i in range(p // 2):
+            q1, q2 = qc[:, 2 * i], qc[:, 2 * i + 1]
+            disc = q2 ** 2 - 4.0 * q1
+            sq = np.where(disc > 0, np.sqrt(np.abs(disc)), 1j * np.sqrt(np.abs(disc)))
+            roots[:, 2 * i] = -0.5 * (q2 + sq)
+            roots[:, 2 * i + 1] = -0.5 * (q2 - sq)
+        if p % 2 == 1:
+            roots[:, -1] = -qc[:, -1]
+        self._samples["ar_roots"] = roots
+        self._samples["psd_width"] = -roots.real / (2.0 * np.pi)
+        self._samples["psd_centroid"] = np.abs(roots.imag) / (2.0 * np.pi)
+
+    def _ar_coefs(self):  # carma_pack.py:500-509
+        roots = self._samples["ar_roots"]
+        self._samples["ar_coefs"] = np.array([np.poly(r).real for r in roots])
+
+    def _ma_coefs(self, trace):  # carma_pack.py:469-498
+        n = trace.shape[0]
+        if self.q == 0:
+            self._samples["ma_coefs"] = np.ones((n, 1))
+            return
+        qc = np.exp(trace[:, 3 + self.p:3 + self.p + self.q])
+        roots = np.empty(qc.shape, dtype=complex)
+        for i in range(self.q // 2):
+            q1, q2 = qc[:, 2 * i], qc[:, 2 * i + 1]
+            disc = q2 ** 2 - 4.0 * q1
+            sq = np.where(disc > 0, np.sqrt(np.abs(disc)), 1j * np.sqrt(np.abs(disc)))
+            roots[:, 2 * i] = -0.5 * (q2 + sq)
+            roots[:, 2 * i + 1] = -0.5 * (q2 - sq)
+        if self.q % 2 == 1:
+            roots[:, -1] = -qc[:, -1]
+        coefs = np.empty((n, self.q + 1))
+        for i in range(n):
+            c = np.poly(roots[i])
+            coefs[i] = (c / c[self.q])[::-1].real
+        self._samples["ma_coefs"] = coefs
+
+    def _sigma_noise(self):  # carma_pack.py:511-546
+        var, roots, ma = self._samples["var"], self._samples["ar_roots"], self._samples["ma_coefs"]
+        total = np.zeros(var.shape[0], dtype=complex)
+        for k in range(self.p):
+            denom = -2.0 * roots[:, k].real + 0j
+            for l in range(self.p):
+                if l != k:
+                    denom = denom * (roots[:, l] - roots[:, k]) * (np.conjugate(roots[:, l]) + roots[:, k])
+            s1 = np.zeros(var.shape[0], dtype=complex)
+            s2 = np.zeros(var.shape[0], dtype=complex)
+            for l in range(ma.shape[1]):
+                s1 += ma[:, l] * roots[:, k] ** l
+                s2 += ma[:, l] * (-roots[:, k]) ** l
+            total += s1 * s2 / denom
+        self._samples["sigma"] = np.sqrt(var / total.real)
+
+    def add_mle(self, MLE):  # carma_pack.py:331-405 (values only)
+        th = np.asarray(MLE.x)[None, :]
+        tmp = CarmaSample.__new__(CarmaSample)
+        MCMCSample.__init__(tmp)
+        tmp.p, tmp.q = self.p, self.q
+        tmp._samples = {"var": th[:, 0] ** 2, "measerr_scale": th[:, 1], "mu": th[:, 2],
+                        "quad_coefs": np.exp(th[:, 3:3 + self.p])}
+        tmp._ar_roots(); tmp._ar_coefs(); tmp._ma_coefs(th); tmp._sigma_noise()
+        self.mle = {k: v[0] for k, v in tmp._samples.items()}
+        self.mle["loglik"] = -MLE.fun
+
+    def _params_at(self, index):
+        roots = self._samples["ar_roots"][index]
+        ma = np.zeros(self.p)
+        mc = self._samples["ma_coefs"][index]
+        ma[:mc.size] = mc
+        sigsqr = float(np.ravel(self._samples["sigma"][index])[0]) ** 2
+        mu = float(np.ravel(self._samples["mu"][index])[0])
+        scale = float(np.ravel(self._samples["measerr_scale"][index])[0])
+        return sigsqr, roots, ma, mu, scale
+
+    def best_index(self):
+        return int(np.argmax(np.ravel(self._samples["logpost"])))
+
+    def predict(self, time, bestfit="map"):
+        """Expected value and variance of the light curve at `time` given the data (carma_pack.py:746-806):
+        all query times in one launch (KalmanFilterp::Predict, one GPU thread per time)."""
+        idx = self.best_index() if bestfit == "map" else int(bestfit)
+        sigsqr, roots, ma, mu, scale = self._params_at(idx)
+        qm, qv = self._series.predict(sigsqr, roots, ma, np.atleast_1d(time), measerr_scale=scale, mu=mu)
+        return qm + mu, qv
+
+    def kalman_filter(self, bestfit="map"):
+        """One-step predictive mean/variance at the data times (assess_fit's ingredients, carma_pack.py:687-744)."""
+        idx = self.best_index() if bestfit == "map" else int(bestfit)
+        sigsqr, roots, ma, mu, scale = self._params_at(idx)
+        mean, var = self._series.filter(sigsqr, roots, ma, measerr_scale=scale, mu=mu)
+        return mean + mu, var
+
+    def DIC(self):  # carma_pack.py:808-828
+        loglik = np.ravel(self._samples["loglik"])
+        return -2.0 * loglik.mean() + 2.0 * np.var(-2.0 * loglik) / 2.0
+
+
+class Car1Sample(MCMCSample):
+    """MCMC samples of a CAR(1) model (carma_pack.py:866-1035, values only)."""
+
+    def __init__(self, time, y, ysig, trace, logpost, series=None, prior=None):
+        super(Car1Sample, self).__init__(trace=trace, logpost=logpost)
+        self.time, self.y, self.ysig = time, y, ysig
+        self.p, self.q = 1, 0
+        trace = np.asarray(trace)
+        self._series = series if series is not None else Series(time, y, ysig)
+        self._prior = prior if prior is not None else self._series.default_prior(True)
+        self._samples["var"] = trace[:, 0] ** 2
+        self._samples["measerr_scale"] = trace[:, 1]
+        self._samples["mu"] = trace[:, 2]
+        self._samples["log_omega"] = trace[:, 3]
+        omega = np.exp(trace[:, 3])
+        self._samples["sigma"] = np.sqrt(2.0 * omega * trace[:, 0] ** 2)
+        self._samples["loglik"] = self._series.loglik(KIND_CAR1, 1, 0, trace, prior=self._prior)
+        self.parameters = list(self._samples.keys())
+        self.newaxis()

@@ -1,0 +1,181 @@
+"""API-surface conformance on the GPU, mirroring the reference's src/tests/testCarmcmc.py
+(10-point series, every overload arity, stored log-posterior == getLogDensity(sample), Predict
+variance grows when extrapolating) plus the CarmaModel drivers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cm():
+    import carma_pack_b200 as c
+    if c._lib.device_count() < 1:
+        pytest.fail("no CUDA device visible")
+    from carma_pack_b200 import _carmcmc
+    c._carmcmc_mod = _carmcmc
+    return c
+
+
+@pytest.fixture(scope="module")
+def small(cm):
+    # testCarmcmc.py:13-34
+    rng = np.random.default_rng(1)
+    npts = 10
+    x = 1.0 * np.arange(npts)
+    ar_roots = np.array([-0.06283185 - 1.25663706j, -0.06283185 + 1.25663706j, -0.02094395 - 0.25132741j,
+                         -0.02094395 + 0.25132741j, -0.03141593 + 0.j])
+    sigsqr = 0.00126811439419
+    y = cm.carma_process(x, sigsqr, ar_roots, rng=rng)
+    dy = np.sqrt(sigsqr) * np.ones(npts)
+    m = cm._carmcmc_mod
+    xd, yd, dyd = m.vecD(), m.vecD(), m.vecD()
+    xd.extend(x); yd.extend(y); dyd.extend(dy)
+    return dict(x=x, y=y, dy=dy, xd=xd, yd=yd, dyd=dyd, nSample=100, nBurnin=10, nThin=1, nWalkers=2)
+
+
+def test_car1_all_arities(cm, small):  # testCarmcmc.py:36-52
+    m = cm._carmcmc_mod
+    s = small
+    m.set_seed(11)
+    cpp = m.run_mcmc_car1(s["nSample"], s["nBurnin"], s["xd"], s["yd"], s["dyd"], s["nThin"])
+    psamples = np.array(cpp.getSamples())
+    plog = np.array(cpp.GetLogLikes())
+    assert psamples.shape == (100, 4) and plog.shape == (100,)
+    sample0 = m.vecD(); sample0.extend(psamples[0])
+    assert np.isfinite(cpp.getLogPrior(sample0))
+    assert abs(plog[0] - cpp.getLogDensity(sample0)) < 1e-7 * max(1, abs(plog[0]))
+    m.run_mcmc_car1(s["nSample"], s["nBurnin"], s["xd"], s["yd"], s["dyd"])
+    guess = cpp.getSamples()[0]
+    m.run_mcmc_car1(s["nSample"], s["nBurnin"], s["xd"], s["yd"], s["dyd"], s["nThin"], guess)
+
+
+@pytest.mark.parametrize("p,q", [(3, 0), (3, 2), (3, 1)])
+def test_carma_all_arities(cm, small, p, q):  # testCarmcmc.py:54-104
+    m = cm._carmcmc_mod
+    s = small
+    m.set_seed(5)
+    a = (s["nSample"], s["nBurnin"], s["xd"], s["yd"], s["dyd"], p, q, s["nWalkers"])
+    m.run_mcmc_carma(*a)
+    m.run_mcmc_carma(*a, False)
+    sampler = m.run_mcmc_carma(*a, False, s["nThin"])
+    psamples = np.array(sampler.getSamples())
+    plog = np.array(sampler.GetLogLikes())
+    assert psamples.shape == (100, 3 + p + q)
+    sample0 = m.vecD(); sample0.extend(psamples[0])
+    assert abs(plog[0] - sampler.getLogDensity(sample0)) < 1e-7 * max(1, abs(plog[0]))
+    guess = sampler.getSamples()[0]
+    again = m.run_mcmc_carma(*a, False, s["nThin"], guess)
+    assert np.array(again.getSamples()).shape == psamples.shape
+    # SetMLE(True): bounds ignored, prior term still added
+    sampler.SetMLE(True)
+    assert np.isfinite(sampler.getLogDensity(sample0))
+    # numpy arrays / lists are accepted where the reference needs vecD
+    assert abs(sampler.getLogDensity(list(psamples[0])) - sampler.getLogDensity(sample0)) == 0.0
+    lp = np.array(sampler.getLogDensityBatch(m.vecvecD([m.vecD(list(r)) for r in psamples[:5]])))
+    assert np.allclose(lp, [sampler.getLogDensity(list(r)) for r in psamples[:5]], rtol=1e-12)
+    # wrong-length init falls back to prior draws with a warning (carpack.cpp:481-484)
+    m.run_mcmc_carma(*a, False, 1, m.vecD([1.0, 2.0]))
+
+
+def test_zcarma_flag_runs_zcar(cm, small):
+    m = cm._carmcmc_mod
+    s = small
+    sampler = m.run_mcmc_carma(50, 10, s["xd"], s["yd"], s["dyd"], 3, 0, 2, True)
+    assert np.array(sampler.getSamples()).shape == (50, 6)
+
+
+def test_kalman1_predict(cm, small):  # testCarmcmc.py:106-117
+    m = cm._carmcmc_mod
+    s = small
+    kf = m.KalmanFilter1(s["xd"], s["yd"], s["dyd"], 1.0, 1.0)
+    kf.Filter()
+    assert len(kf.GetMean()) == 10 and len(kf.GetVar()) == 10
+    pred0 = kf.Predict(s["xd"][0])
+    predN = kf.Predict(s["xd"][-1] + 1)
+    assert predN.second > pred0.second
+    sim = np.array(kf.Simulate(m.vecD([0.5, 3.3, 12.0])))
+    assert sim.shape == (3,) and np.all(np.isfinite(sim))
+
+
+def test_kalmanp_predict_and_golden(cm, small, kelly):  # testCarmcmc.py:119-146
+    m = cm._carmcmc_mod
+    s = small
+    sampler = m.run_mcmc_carma(s["nSample"], s["nBurnin"], s["xd"], s["yd"], s["dyd"], 4, 0, s["nWalkers"], False, 1)
+    trace = np.array(sampler.getSamples())
+    smp = cm.CarmaSample(s["x"], s["y"], s["dy"], trace=trace, logpost=np.array(sampler.GetLogLikes()), p=4, q=0)
+    sigsqr = float(smp._samples["sigma"][0][0]) ** 2
+    omega = m.vecC()
+    for r in smp._samples["ar_roots"][0]:
+        omega.append(complex(r))
+    ma = m.vecD([1.0, 0.0, 0.0, 0.0])
+    kf = m.KalmanFilterp(s["xd"], s["yd"], s["dyd"], sigsqr, omega, ma)
+    kf.Filter()
+    pred0 = kf.Predict(s["xd"][0])
+    predN = kf.Predict(s["xd"][-1] + 1)
+    assert predN.second > pred0.second
+    # the class API reproduces the golden filter of the reference (carma_unit_tests.cpp:387-444)
+    kf = m.KalmanFilterp(m.vecD(kelly["t"]), m.vecD(kelly["y"]), m.vecD(kelly["yerr"]), float(kelly["sigsqr"]),
+                         m.vecC([complex(z) for z in kelly["roots"]]), m.vecD(kelly["ma"]))
+    kf.Filter()
+    np.testing.assert_allclose(np.array(kf.GetVar()), kelly["var"], rtol=1e-9)
+    np.testing.assert_allclose(np.array(kf.GetMean()), kelly["mean"], rtol=0, atol=1e-9)
+    pm, pv = kf.PredictMany(m.vecD(kelly["predict_t"]))
+    np.testing.assert_allclose(np.array(pm), kelly["predict_mean"], rtol=1e-7, atol=1e-9)
+    # unsorted input with a duplicate time is sorted and de-duplicated like KalmanFilter::init (kfilter.hpp:43-76)
+    t2 = np.concatenate([kelly["t"][:50][::-1], kelly["t"][:1]])
+    y2 = np.concatenate([kelly["y"][:50][::-1], kelly["y"][:1]])
+    e2 = np.concatenate([kelly["yerr"][:50][::-1], kelly["yerr"][:1]])
+    kf2 = m.KalmanFilterp(m.vecD(t2), m.vecD(y2), m.vecD(e2), float(kelly["sigsqr"]),
+                          m.vecC([complex(z) for z in kelly["roots"]]), m.vecD(kelly["ma"]))
+    kf2.Filter()
+    assert len(kf2.GetVar()) == 50
+    np.testing.assert_allclose(np.array(kf2.GetVar()), kelly["var"][:50], rtol=1e-9)
+
+
+def test_carma_model_run_mcmc_and_sample(cm):
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(120, 21)
+    model = cm.CarmaModel(t, y, e, p=3, q=1)
+    sample = model.run_mcmc(300, nburnin=300, seed=3, n_ensembles=4)
+    assert sample._samples["logpost"].shape == (1200, 1)
+    for k in ("ar_roots", "psd_centroid", "psd_width", "ar_coefs", "ma_coefs", "sigma", "var", "mu", "loglik"):
+        assert k in sample.parameters
+    # loglik (SetMLE) = logpost for in-prior samples: same prior term is added
+    np.testing.assert_allclose(sample._samples["loglik"], sample._samples["logpost"], rtol=1e-8)
+    tq = np.linspace(t[0] - 5, t[-1] + 20, 64)
+    pm, pv = sample.predict(tq)
+    assert pm.shape == (64,) and np.all(pv > 0) and pv[-1] > pv[len(pv) // 2]
+    mean, var = sample.kalman_filter()
+    chi = (y - mean) / np.sqrt(var)
+    assert 0.5 < chi.std() < 2.0  # standardized residuals are O(1) (assess_fit, carma_pack.py:687-744)
+    assert np.isfinite(sample.DIC())
+    # CAR(1) path
+    m1 = cm.CarmaModel(t, y, e, p=1)
+    s1 = m1.run_mcmc(200, seed=4)
+    assert s1._samples["log_omega"].shape == (200, 1)
+
+
+def test_choose_order_small_grid(cm):
+    """choose_order over p <= 2: AICc bookkeeping as carma_pack.py:173-190 and MLEs at least as good as
+    the best random start; the GPU MLE log-likelihood is reproduced by the CPU oracle."""
+    from carma_pack_b200 import synth
+    from oracle import oracle as O
+    rng = np.random.default_rng(2)
+    t = np.cumsum(rng.uniform(0.5, 1.5, 200))
+    y = 1.0 + synth.car1_process(t, 2 * 1.2 ** 2 / 8.0, 8.0, rng)
+    e = np.full(t.size, 0.1)
+    y = y + e * rng.standard_normal(t.size)
+    model = cm.CarmaModel(t, y, e)
+    mle, pqlist, aicc = model.choose_order(2, ntrials=24, seed=7, verbose=False)
+    assert pqlist == [(1, 0), (2, 0), (2, 1)]
+    assert (model.p, model.q) == pqlist[int(np.argmin(aicc))]
+    assert all(np.isfinite(aicc))
+    # CAR(1) data: CAR(1) is competitive and its MLE sits near the truth
+    m1 = model.get_mle(1, 0, ntrials=24, seed=8)
+    assert abs(m1.x[3] - np.log(1 / 8.0)) < 1.0
+    pr = O.default_prior(t, y)
+    want = O.logdensity(O.KIND_CAR1, 1, 0, t, y, e, m1.x, prior=pr)[0]
+    assert abs(-m1.fun - want) < 1e-8 * abs(want)
+    k = 2 + 1
+    assert abs(aicc[0] - (2 * k + 2 * model.get_mle(1, 0, ntrials=24, seed=7).fun + 2 * k * (k + 1) / (t.size - k - 1))) < 0.5
