@@ -35,26 +35,47 @@ def to_prior(C, opr):
     return C.Prior(opr.max_stdev, opr.max_freq, opr.min_freq, opr.kappa_low, opr.kappa_high, opr.measerr_dof)
 
 
-def assert_logpost_parity(got, want, want_ld=None, rtol=RTOL, max_illcond_frac=0.002, what=""):
+def assert_logpost_parity(got, want, want_ld=None, rtol=RTOL, max_illcond_frac=0.002, what="", ulp_eval=None):
+    """got vs want at rtol.  Rows that miss rtol are accepted only if the REFERENCE algorithm is itself
+    not reproducible to rtol there, measured two ways: (a) |double - long double| of the oracle, and
+    (b) `ulp_eval(rows, k)` = the oracle re-evaluated with every theta component moved by k ulps
+    (the device exp() legitimately differs from glibc's by an ulp, which moves near-degenerate roots).
+    Such rows are counted and must stay below max_illcond_frac."""
     got, want = np.asarray(got), np.asarray(want)
     fin_w, fin_g = np.isfinite(want), np.isfinite(got)
     # same class: finite / -inf / nan
     assert np.array_equal(fin_w, fin_g), "%s: finite-class mismatch at %s" % (what, np.where(fin_w != fin_g)[0][:10])
     ninf_w, ninf_g = want == -np.inf, got == -np.inf
     assert np.array_equal(ninf_w, ninf_g), "%s: -inf class mismatch" % what
+    idx = np.nonzero(fin_w)[0]
     err = np.abs(got[fin_w] - want[fin_w])
     tol = rtol * np.maximum(np.abs(want[fin_w]), 1.0)
     bad = err > tol
     if want_ld is None:
         assert not bad.any(), "%s: max rel err %.3e" % (what, np.max(err / np.maximum(np.abs(want[fin_w]), 1.0)))
         return 0
-    # rows where the reference algorithm itself is not reproducible to rtol in double precision
     noise = np.abs(np.asarray(want_ld)[fin_w] - want[fin_w])
+    if ulp_eval is not None and bad.any():
+        rows = idx[bad]
+        for k in (1, -1, 2, -2):
+            pert = ulp_eval(rows, k)
+            dlt = np.abs(pert - want[rows])
+            noise[bad] = np.maximum(noise[bad], np.where(np.isfinite(dlt), dlt, np.inf))
     really_bad = bad & (err > 50.0 * noise + tol)
-    assert not really_bad.any(), "%s: %d rows differ beyond tolerance and beyond the oracle's own noise floor" % (
-        what, really_bad.sum())
+    assert not really_bad.any(), "%s: %d rows differ beyond tolerance and beyond the oracle's own noise floor: %s" % (
+        what, really_bad.sum(), idx[really_bad][:10])
     assert bad.mean() <= max_illcond_frac, "%s: %.4f of rows needed the noise-floor criterion" % (what, bad.mean())
     return int(bad.sum())
+
+
+def ulp_shift(theta, k):
+    """Move every component k ulps (alternating direction by column so the perturbation is generic)."""
+    th = np.array(theta, dtype=np.float64)
+    sign = np.where(np.arange(th.shape[1]) % 2 == 0, 1.0, -1.0) * np.sign(k)
+    out = th.copy()
+    for _ in range(abs(k)):
+        out = np.nextafter(out, out + sign[None, :] * np.inf)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,7 +214,9 @@ def test_loglik_config2_65536_thetas(C, O):
     want = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr)
     assert 0.5 < np.isfinite(want).mean() < 1.0  # both the filter path and the -inf early-out are exercised
     want_ld = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr, long_double=True)
-    n_ill = assert_logpost_parity(got, want, want_ld, what="config2")
+    n_ill = assert_logpost_parity(
+        got, want, want_ld, what="config2",
+        ulp_eval=lambda rows, k: O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, ulp_shift(th[rows], k), prior=opr))
     print("config2: %d of 65536 rows used the noise-floor criterion" % n_ill)
     # idempotence / determinism: same input, same bits
     got2 = s.loglik(C.KIND_CARMA, 5, 3, th, prior=pr)
@@ -213,7 +236,9 @@ def test_loglik_long_series_chunked_pipeline(C, O, kelly):
         got = s.loglik(C.KIND_CARMA, 5, 3, th)
         want = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th)
         want_ld = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, long_double=True)
-        assert_logpost_parity(got, want, want_ld, max_illcond_frac=0.02, what="ny=%d" % ny)
+        assert_logpost_parity(
+            got, want, want_ld, max_illcond_frac=0.02, what="ny=%d" % ny,
+            ulp_eval=lambda rows, k: O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, ulp_shift(th[rows], k)))
         assert got[0] == got[1] or (np.isnan(got[0]) and np.isnan(got[1]))
         s.close()
     # kelly fixture through LogDensity-like path is covered by the golden filter test; here the
@@ -302,7 +327,9 @@ def _check_trace_against_oracle(C, O, res, kind, p, q, t, y, e, opr, ntemps, tma
     d = prop.shape[-1]
     lp_o = O.logdensity(kind, p, q, t, y, e, prop.reshape(-1, d), prior=opr).reshape(iters, ntemps)
     lp_ld = O.logdensity(kind, p, q, t, y, e, prop.reshape(-1, d), prior=opr, long_double=True).reshape(iters, ntemps)
-    assert_logpost_parity(rt["lp_prop"].ravel(), lp_o.ravel(), lp_ld.ravel(), max_illcond_frac=0.01, what="pt proposals")
+    flat = prop.reshape(-1, d)
+    assert_logpost_parity(rt["lp_prop"].ravel(), lp_o.ravel(), lp_ld.ravel(), max_illcond_frac=0.01, what="pt proposals",
+                          ulp_eval=lambda rows, k: O.logdensity(kind, p, q, t, y, e, ulp_shift(flat[rows], k), prior=opr))
     nflip = 0
     for it in range(iters):
         for c in range(ntemps):
