@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--no-pt", action="store_true", help="skip the PT-MCMC secondary measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU baseline")
     ap.add_argument("--pt-ensembles", type=int, default=4096)
-    ap.add_argument("--pt-iters", type=int, default=20)
+    ap.add_argument("--pt-iters", type=int, default=100)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -4,7 +4,9 @@
   carma_pack_b200/_carmcmc*.so       pybind11 module re-exporting the reference's `_carmcmc`
                                      surface on top of the C ABI                         (g++)
 
-Run as  `python -m carma_pack_b200.build`  or through  __graft_entry__.build().
+Run as  `python build_native.py [--force] [-v]`  or through  __graft_entry__.build().  Lives outside the
+package on purpose: importing carma_pack_b200 loads libcarma_b200.so and must fail loudly when it is
+missing, so the thing that creates the library cannot be inside it.
 """
 import os
 import shutil
@@ -12,15 +14,15 @@ import subprocess
 import sys
 import sysconfig
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, "carma_pack_b200")
 CSRC = os.path.join(HERE, "csrc")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = os.environ.get("CXX_HOST") or shutil.which("g++") or "g++"
 
 CUDA_SOURCES = ["loglik.cu", "mcmc.cu"]
-CUDA_HEADERS = ["device_math.cuh", "theta_transform.cuh", "kalman_real.cuh", "kalman_cplx.cuh", "series.h",
+CUDA_HEADERS = ["device_math.cuh", "fast_math.cuh", "theta_transform.cuh", "kalman_real.cuh", "kalman_cplx.cuh", "series.h",
                 os.path.join(ROOT, "include", "carma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

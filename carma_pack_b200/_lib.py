@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev",
-    "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev",
+    "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
 ]
 
 
@@ -63,7 +63,7 @@ _sz = ctypes.c_size_t
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "carma_pack_b200: %s is missing. Build it with `python -m carma_pack_b200.build` "
+            "carma_pack_b200: %s is missing. Build it with `python build_native.py` "
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     L = ctypes.CDLL(LIB_PATH)
     L.carma_last_error.restype = ctypes.c_char_p
@@ -94,6 +94,7 @@ def _load():
                                    _vp, _vp, _vp, _vp, _vp, _vp]
     L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
     L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
+    L.carma_fastmath_dev.argtypes = [_dp, _sz, _dp, _dp, _dp, _dp]
     L.carma_tdist_dev.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _dp]
     return L
 
@@ -318,3 +319,10 @@ def tdist_dev(seed, chain, it, j, dof=8):
     out = ctypes.c_double()
     check(lib.carma_tdist_dev(seed, chain, it, j, dof, ctypes.byref(out)), "carma_tdist_dev")
     return out.value
+
+
+def fastmath_dev(x):
+    x = _c(x)
+    e, s, c, r = (np.empty(x.size) for _ in range(4))
+    check(lib.carma_fastmath_dev(_ptr(x), x.size, _ptr(e), _ptr(s), _ptr(c), _ptr(r)), "carma_fastmath_dev")
+    return e, s, c, r

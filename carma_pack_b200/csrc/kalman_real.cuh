@@ -17,6 +17,7 @@
 //     var = c.g + yerr^2, and the predict step is D <- Phi D Phi^T (no subtract/add of V);
 //   * g is computed once per step and reused for the gain, the state update and the variance.
 #pragma once
+#include "fast_math.cuh"
 #include "theta_transform.cuh"
 
 namespace carma {
@@ -45,6 +46,9 @@ struct KalmanReal {
 
     // One Update(): condition on the residual `innov` (= y_i - mu - mean_i) observed with predictive
     // variance `var`, move forward by dt, and form mean/var for the next point (measurement variance e2n).
+    // ALLC = true: every 2x2 slot is a conjugate pair (compile-time straight-line code, the common case);
+    // ALLC = false: per-slot run-time selection between conjugate pair and real pair.
+    template <bool ALLC>
     __device__ __forceinline__ void advance(const RealParams<P>& prm, double innov, double inv_var, double dt,
                                             double e2n) {
         // ---- measurement update:  z += g innov/var ;  D -= g g^T / var
@@ -64,17 +68,19 @@ struct KalmanReal {
         double f00[NS > 0 ? NS : 1], f01[NS > 0 ? NS : 1], f10[NS > 0 ? NS : 1], f11[NS > 0 ? NS : 1];
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            if ((prm.cmask >> s) & 1u) {
-                double e = exp(prm.lam[2 * s] * dt);
+            // the decay factor of the first root is common to both slot types
+            double e = exp_fast(prm.lam[2 * s] * dt);
+            if (ALLC || ((prm.cmask >> s) & 1u)) {
                 double sn, cs;
-                sincos(prm.lam[2 * s + 1] * dt, &sn, &cs);
+                sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
                 f00[s] = e * cs; f01[s] = -(e * sn); f10[s] = e * sn; f11[s] = e * cs;
             } else {
-                f00[s] = exp(prm.lam[2 * s] * dt); f01[s] = 0.0; f10[s] = 0.0; f11[s] = exp(prm.lam[2 * s + 1] * dt);
+                f00[s] = e; f01[s] = 0.0; f10[s] = 0.0;
+                f11[s] = exp_fast(prm.lam[2 * s + 1] * dt);
             }
         }
         double fo = 1.0;
-        if (ODD) fo = exp(prm.lam[P - 1] * dt);
+        if (ODD) fo = exp_fast(prm.lam[P - 1] * dt);
 
         // ---- predict state
 #pragma unroll
@@ -164,21 +170,34 @@ struct LogLikAcc {
 
 // Run the recursion over `len` staged points (dt, y, next-point yerr^2); the last `len - nadv`
 // (0 or 1) points are only scored, not advanced past (end of the light curve).
+template <int P, bool ALLC>
+__device__ __forceinline__ void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
+                                                 const double* __restrict__ sdt, const double* __restrict__ sy,
+                                                 const double* __restrict__ se, int len, int nadv) {
+    for (int i = 0; i < nadv; i++) {
+        double innov = (sy[i] - prm.mu) - kf.mean;
+        double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+        kf.template advance<ALLC>(prm, innov, inv, sdt[i], se[i]);
+    }
+    if (nadv < len) {
+        double innov = (sy[len - 1] - prm.mu) - kf.mean;
+        double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+    }
+}
+
 template <int P>
 __device__ __forceinline__ void filter_span(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
                                             const double* __restrict__ sdt, const double* __restrict__ sy,
                                             const double* __restrict__ se, int len, int nadv) {
-    for (int i = 0; i < nadv; i++) {
-        double innov = (sy[i] - prm.mu) - kf.mean;
-        double inv = 1.0 / kf.var;
-        acc.add(kf.var, innov, inv);
-        kf.advance(prm, innov, inv, sdt[i], se[i]);
-    }
-    if (nadv < len) {
-        double innov = (sy[len - 1] - prm.mu) - kf.mean;
-        double inv = 1.0 / kf.var;
-        acc.add(kf.var, innov, inv);
-    }
+    constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
+    // Warp-uniform choice: the straight-line all-conjugate-pairs loop only when EVERY active lane of the
+    // warp qualifies; otherwise all lanes run the generic loop (per-slot selection, reconverging each
+    // slot).  A per-lane choice would execute both loops back to back in a mixed warp.
+    const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
+    if (all_c) filter_span_impl<P, true>(kf, acc, prm, sdt, sy, se, len, nadv);
+    else filter_span_impl<P, false>(kf, acc, prm, sdt, sy, se, len, nadv);
 }
 
 }  // namespace carma

@@ -163,20 +163,8 @@ multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y,
     LogLikAcc acc;
     kf.reset(prm, e2[o0]);
     acc.init();
-    const double* pdt = dt + o0;
-    const double* py = y + o0;
-    const double* pe = e2 + o0;
-    for (int i = 0; i < ny - 1; i++) {
-        double innov = (py[i] - prm.mu) - kf.mean;
-        double inv = 1.0 / kf.var;
-        acc.add(kf.var, innov, inv);
-        kf.advance(prm, innov, inv, pdt[i], pe[i + 1]);
-    }
-    {
-        double innov = (py[ny - 1] - prm.mu) - kf.mean;
-        double inv = 1.0 / kf.var;
-        acc.add(kf.var, innov, inv);
-    }
+    // e2 of the NEXT point is needed at step i: pass the array shifted by one
+    filter_span<P>(kf, acc, prm, dt + o0, y + o0, e2 + o0 + 1, ny, ny - 1);
     out[c] = acc.value() + prm.logprior;
 }
 
@@ -299,6 +287,18 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     }
     double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
     if (s == 12345.678) out[0] = s;
+}
+
+__global__ void fastmath_kernel(const double* __restrict__ x, size_t n, double* __restrict__ e, double* __restrict__ sn,
+                                double* __restrict__ cs, double* __restrict__ rc) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    e[i] = exp_fast(x[i]);
+    double s, c;
+    sincos_fast(x[i], &s, &c);
+    sn[i] = s;
+    cs[i] = c;
+    rc[i] = rcp_fast(x[i]);
 }
 
 __global__ void philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out) {
@@ -661,6 +661,24 @@ int carma_fp64_peak_tflops(int device, double* tflops) {
     cudaFree(d_out);
     *tflops = best;
     return CARMA_OK;
+}
+
+int carma_fastmath_dev(const double* x, size_t n, double* out_exp, double* out_sin, double* out_cos, double* out_rcp) {
+    if (!x || !out_exp || !out_sin || !out_cos || !out_rcp) return CARMA_ERR_ARG;
+    if (n == 0) return CARMA_OK;
+    double* d = nullptr;
+    if (!cuda_ok(cudaMalloc((void**)&d, 5 * n * sizeof(double)), "cudaMalloc")) return CARMA_ERR_CUDA;
+    bool ok = cuda_ok(cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice), "H2D x");
+    if (ok) {
+        fastmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, n, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+        ok = cuda_ok(cudaGetLastError(), "fastmath_kernel launch") &&
+             cuda_ok(cudaMemcpy(out_exp, d + n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
+             cuda_ok(cudaMemcpy(out_sin, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
+             cuda_ok(cudaMemcpy(out_cos, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
+             cuda_ok(cudaMemcpy(out_rcp, d + 4 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H");
+    }
+    cudaFree(d);
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
 }
 
 int carma_philox_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out4) {

@@ -118,9 +118,11 @@ __device__ void starting_ar(StartRng& g, const PTParams& pp, double* loga) {
     if (P & 1) loga[P - 1] = log(2.0 * PI * width[P / 2]);
 }
 
+// __noinline__: one copy of the filter loop per kernel (three call sites), with its own register
+// allocation, so the MCMC bookkeeping around it does not inflate the per-thread register count.
 template <int P>
-__device__ double logdensity_resident(const PTParams& pp, const double* th, const double* sdt, const double* sy,
-                                      const double* se, double e2_0) {
+__device__ __noinline__ double logdensity_resident(const PTParams& pp, const double* th, const double* sdt,
+                                                   const double* sy, const double* se, double e2_0) {
     RealParams<P> prm;
     if (transform_theta<P>(pp.kind, pp.q, 0u, pp.prior, th, prm) != TT_OK) return -INFINITY;
     KalmanReal<P> kf;
@@ -163,7 +165,7 @@ __device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double
 __device__ __forceinline__ int tri(int k, int j) { return j * (j + 1) / 2 + k; }  // k <= j
 
 template <int P>
-__global__ void __launch_bounds__(PT_BLOCK) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
+__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 7 : (P == 6 ? 5 : 4))) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 

@@ -190,6 +190,10 @@ int carma_fp64_peak_tflops(int device, double* tflops);
 int carma_philox_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out4);
 int carma_tdist_dev(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, int dof, double* out);
 
+/* The branch-free exp / sincos / reciprocal used inside the Kalman time loop (csrc/fast_math.cuh),
+ * evaluated element-wise on host arrays, so tests can bound their error against libm. */
+int carma_fastmath_dev(const double* x, size_t n, double* out_exp, double* out_sin, double* out_cos, double* out_rcp);
+
 #ifdef __cplusplus
 }
 #endif

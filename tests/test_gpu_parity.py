@@ -315,6 +315,26 @@ def test_philox_bit_exact_and_tdist(C, O):
         assert abs(a - b) <= 1e-13 * max(1.0, abs(b))
 
 
+def test_fast_math_accuracy(C):
+    """exp_fast / sincos_fast / rcp_fast (csrc/fast_math.cuh) against numpy in long double."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-np.exp(rng.uniform(np.log(1e-8), np.log(700.0), 20000)), [0.0, -1e-300, -708.0, -745.0, -1e4],
+                        rng.uniform(-1.0, 1.0, 2000)])
+    e, _, _, _ = C._lib.fastmath_dev(x)
+    want = np.exp(x.astype(np.longdouble))
+    big = want > 1e-300
+    rel = np.abs(e[big] - want[big]) / want[big]
+    assert rel.max() < 4e-16, rel.max()
+    assert np.all(e[~big] >= 0) and np.all(e[~big] < 1e-299)   # flushed region
+    xs = np.concatenate([rng.uniform(-1e5, 1e5, 20000), rng.uniform(-10, 10, 5000), [0.0, 1e9, -3.3e12]])
+    _, s, c, _ = C._lib.fastmath_dev(xs)
+    ws, wc = np.sin(xs.astype(np.longdouble)), np.cos(xs.astype(np.longdouble))
+    assert np.abs(s - ws).max() < 4e-16 and np.abs(c - wc).max() < 4e-16
+    xr = np.concatenate([np.exp(rng.uniform(np.log(1e-200), np.log(1e200), 20000)), -np.exp(rng.uniform(-5, 5, 100))])
+    _, _, _, r = C._lib.fastmath_dev(xr)
+    assert (np.abs(r * xr - 1.0)).max() < 5e-16
+
+
 # ------------------------------------------------------------------------------------------------
 # PT-MCMC
 # ------------------------------------------------------------------------------------------------
