@@ -150,7 +150,19 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        # NCCL announces its version on stdout when the communicator is created; keep stdout for the
+        # single JSON line by pointing fd 1 at stderr while the communicator comes up.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     t, y, e, th = make_inputs(seed_offset=rank)
     series = C.Series(t, y, e, device=dev)
