@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = os.environ.get("CXX_HOST") or shutil.which("g++") or "g++"
 
-CUDA_SOURCES = ["loglik.cu", "mcmc.cu"]
+CUDA_SOURCES = ["loglik.cu", "mcmc.cu", "scan.cu"]
 CUDA_HEADERS = ["device_math.cuh", "fast_math.cuh", "theta_transform.cuh", "kalman_real.cuh", "kalman_cplx.cuh", "series.h",
                 os.path.join(ROOT, "include", "carma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -54,13 +54,20 @@ def build_cuda(force=False, verbose=False):
     if not force and not _newer(LIB, deps):
         return LIB
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    objs = []
-    for s in srcs:
-        o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
-        out = _run([NVCC] + NVCC_FLAGS + ["-c", s, "-o", o], log=o + ".log")
-        if verbose:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
+        o = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        if not force and not _newer(o, [src] + deps[len(srcs):]):
+            return o, ""
+        return o, _run([NVCC] + NVCC_FLAGS + ["-c", src, "-o", o], log=o + ".log")
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+        results = list(ex.map(compile_one, srcs))
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, out in results:
             print(out)
-        objs.append(o)
     _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"])
     return LIB
 

@@ -19,7 +19,7 @@ MAX_P = 7
 EXPORTED_SYMBOLS = [
     "carma_last_error", "carma_abi_version", "carma_device_count",
     "carma_series_create", "carma_series_destroy", "carma_series_length", "carma_series_default_prior",
-    "carma_loglik_batch_dev", "carma_loglik_batch", "carma_log_prior",
+    "carma_loglik_batch_dev", "carma_loglik_batch", "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
@@ -75,6 +75,10 @@ def _load():
     L.carma_loglik_batch_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp,
                                          ctypes.c_uint, _vp]
     L.carma_loglik_batch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp, ctypes.c_uint]
+    L.carma_loglik_scan_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp,
+                                        ctypes.c_uint, ctypes.c_int, _vp]
+    L.carma_loglik_scan.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp, ctypes.c_uint,
+                                    ctypes.c_int]
     L.carma_log_prior.argtypes = [ctypes.c_int, ctypes.c_int, _dp, pr, _dp]
     L.carma_multi_series_create.argtypes = [_dp, _dp, _dp, ctypes.POINTER(ctypes.c_int64), _sz, ctypes.c_int,
                                             ctypes.POINTER(_vp)]
@@ -174,6 +178,23 @@ class Series:
         check(lib.carma_loglik_batch(self.handle, kind, p, q, ctypes.byref(prior), th.shape[0],
                                      th.ctypes.data, out.ctypes.data, flags), "carma_loglik_batch")
         return out
+
+    def loglik_scan(self, kind, p, q, theta, prior=None, flags=0, chunk=0):
+        """Same value as loglik(), computed by the temporally parallel scan (for one very long series)."""
+        th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        d = model_dim(kind, p, q)
+        if th.shape[1] != d:
+            raise ValueError("theta must have %d columns for this model, got %d" % (d, th.shape[1]))
+        if prior is None:
+            prior = self.default_prior()
+        out = np.empty(th.shape[0])
+        check(lib.carma_loglik_scan(self.handle, kind, p, q, ctypes.byref(prior), th.shape[0], th.ctypes.data,
+                                    out.ctypes.data, flags, chunk), "carma_loglik_scan")
+        return out
+
+    def loglik_scan_dev(self, kind, p, q, d_theta_ptr, d_out_ptr, n, prior, flags=0, chunk=0, stream=0):
+        check(lib.carma_loglik_scan_dev(self.handle, kind, p, q, ctypes.byref(prior), n, d_theta_ptr, d_out_ptr, flags,
+                                        chunk, stream), "carma_loglik_scan_dev")
 
     def loglik_dev(self, kind, p, q, d_theta_ptr, d_out_ptr, n, prior, flags=0, stream=0):
         """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr()), no sync."""

@@ -51,7 +51,12 @@ struct KalmanReal {
     template <bool ALLC>
     __device__ __forceinline__ void advance(const RealParams<P>& prm, double innov, double inv_var, double dt,
                                             double e2n) {
-        // ---- measurement update:  z += g innov/var ;  D -= g g^T / var
+        measurement_update(innov, inv_var);
+        predict_observe<ALLC>(prm, dt, e2n);
+    }
+
+    // z += g innov/var ;  D -= g g^T / var   (kfilter.cpp:191-197)
+    __device__ __forceinline__ void measurement_update(double innov, double inv_var) {
         const double w = innov * inv_var;
         double gi[P];
 #pragma unroll
@@ -63,7 +68,11 @@ struct KalmanReal {
         for (int i = 0; i < P; i++)
 #pragma unroll
             for (int j = i; j < P; j++) D[idx(i, j)] = fma(-gi[i], g[j], D[idx(i, j)]);
+    }
 
+    // transition by dt and predicted observation of the next point (kfilter.cpp:200-210)
+    template <bool ALLC>
+    __device__ __forceinline__ void predict_observe(const RealParams<P>& prm, double dt, double e2n) {
         // ---- transition blocks Phi_s
         double f00[NS > 0 ? NS : 1], f01[NS > 0 ? NS : 1], f10[NS > 0 ? NS : 1], f11[NS > 0 ? NS : 1];
 #pragma unroll

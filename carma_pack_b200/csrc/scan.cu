@@ -1,0 +1,538 @@
+// scan.cu -- K5: temporally parallel (associative-scan) CARMA Kalman log-likelihood for ONE very long
+// light curve (BASELINE config 5: ny = 10^6).  The reference filter is a strictly sequential
+// recurrence over time (kfilter.hpp:126-132); every other configuration has abundant batch
+// parallelism and uses the sequential-in-registers kernels, this one has none.
+//
+// Formulation: Sarkka & Garcia-Fernandez (2021) filtering elements a_k = (A, b, C, eta, J) in the
+// real half of the rotated state space (theta_transform.cuh), with the associative operator
+//     A_ij = A_j M A_i                 b_ij = A_j M (b_i + C_i eta_j) + b_j
+//     C_ij = A_j M C_i A_j^T + C_j     eta_ij = A_i^T M^T (eta_j - J_j b_i) + eta_i
+//     J_ij = A_i^T M^T J_j A_i + J_i    M = (I + C_i J_j)^{-1}
+// The prefix a_0 (x) ... (x) a_k carries the filtered mean and covariance (b, C) after point k.
+//
+// Three passes, O(ny) work, O(ny / chunk) parallelism:
+//   1. scan_reduce_kernel : one thread per chunk of `chunk` consecutive points folds its per-point
+//      elements into one aggregate.  The right operand is always a single-point element (J_j = w w^T/S
+//      is rank one), so M comes from Sherman-Morrison: no matrix inverse in this pass.
+//   2. scan_prefix_kernel : one block scans the aggregates (general operator, Gauss-Jordan inverse with
+//      partial pivoting on a PxP matrix) and emits the filtered state in front of every chunk.
+//   3. scan_filter_kernel : one thread per chunk re-runs the ordinary sequential filter (KalmanReal,
+//      the same code as K1) from that state and sums its chunk's log-likelihood terms.
+//   4. scan_sum_kernel    : fixed-order reduction of the chunk sums (+ log-prior): deterministic.
+#include <algorithm>
+#include <cmath>
+#include <string>
+
+#include "kalman_real.cuh"
+#include "series.h"
+
+namespace carma {
+
+template <int P>
+struct ScanParams {
+    RealParams<P> prm;
+    double V[P][P];  // stationary covariance, real basis
+    int status;      // TT_OK / TT_NEG_INF
+};
+
+template <int P>
+struct ScanElem {
+    double A[P][P], b[P], C[P][P], eta[P], J[P][P];
+};
+template <int P>
+struct FiltState {
+    double b[P], C[P][P];
+};
+
+template <int P>
+__global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma_prior_t prior,
+                                   const double* __restrict__ theta, ScanParams<P>* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double th[MAX_D];
+    for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[j] : 0.0;
+    double Vr[P * (P + 1) / 2];
+    RealParams<P> prm;
+    int st = transform_theta<P, true>(kind, q, flags, prior, th, prm, Vr);
+    out->status = st;
+    out->prm = prm;
+    int o = 0;
+    for (int m = 0; m < P; m++)
+        for (int n = m; n < P; n++) { out->V[m][n] = Vr[o]; out->V[n][m] = Vr[o]; o++; }
+}
+
+// dense transition matrix Phi(dt) in the real basis
+template <int P>
+__device__ void build_phi(const RealParams<P>& prm, double dt, double F[P][P]) {
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) F[i][j] = 0.0;
+    for (int s = 0; s < P / 2; s++) {
+        double e = exp_fast(prm.lam[2 * s] * dt);
+        if ((prm.cmask >> s) & 1u) {
+            double sn, cs;
+            sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
+            F[2 * s][2 * s] = e * cs; F[2 * s][2 * s + 1] = -(e * sn);
+            F[2 * s + 1][2 * s] = e * sn; F[2 * s + 1][2 * s + 1] = e * cs;
+        } else {
+            F[2 * s][2 * s] = e;
+            F[2 * s + 1][2 * s + 1] = exp_fast(prm.lam[2 * s + 1] * dt);
+        }
+    }
+    if (P & 1) F[P - 1][P - 1] = exp_fast(prm.lam[P - 1] * dt);
+}
+
+// per-point quantities of point k >= 1 reached from k-1 by dt:  Q = V - F V F^T, w = F^T c, Qc, S, K
+template <int P>
+struct StepOps {
+    double F[P][P], Q[P][P], w[P], Qc[P], K[P], S;
+    __device__ void build(const ScanParams<P>& sp, double dt, double r) {
+        build_phi<P>(sp.prm, dt, F);
+        double FV[P][P];
+        for (int i = 0; i < P; i++)
+            for (int j = 0; j < P; j++) {
+                double s = 0.0;
+                for (int k = 0; k < P; k++) s = fma(F[i][k], sp.V[k][j], s);
+                FV[i][j] = s;
+            }
+        for (int i = 0; i < P; i++)
+            for (int j = 0; j < P; j++) {
+                double s = 0.0;
+                for (int k = 0; k < P; k++) s = fma(FV[i][k], F[j][k], s);
+                Q[i][j] = sp.V[i][j] - s;
+            }
+        S = r;
+        for (int i = 0; i < P; i++) {
+            double a = 0.0, q = 0.0;
+            for (int k = 0; k < P; k++) { a = fma(F[k][i], sp.prm.c[k], a); q = fma(Q[i][k], sp.prm.c[k], q); }
+            w[i] = a;
+            Qc[i] = q;
+        }
+        for (int i = 0; i < P; i++) S = fma(sp.prm.c[i], Qc[i], S);
+        for (int i = 0; i < P; i++) K[i] = Qc[i] / S;
+    }
+};
+
+// element of a single point k >= 1
+template <int P>
+__device__ void single_elem(const ScanParams<P>& sp, const StepOps<P>& o, double y, ScanElem<P>& e) {
+    for (int i = 0; i < P; i++) {
+        for (int j = 0; j < P; j++) {
+            double kcF = 0.0;  // (K c^T F)[i][j] = K_i * (c^T F)_j = K_i * w_j
+            kcF = o.K[i] * o.w[j];
+            e.A[i][j] = o.F[i][j] - kcF;
+            e.C[i][j] = o.Q[i][j] - o.K[i] * o.Qc[j];
+            e.J[i][j] = o.w[i] * o.w[j] / o.S;
+        }
+        e.b[i] = o.K[i] * y;
+        e.eta[i] = o.w[i] * y / o.S;
+    }
+}
+
+// element of point 0: Kalman update of the stationary prior (A = 0, eta = 0, J = 0)
+template <int P>
+__device__ void first_elem(const ScanParams<P>& sp, double y, double r, ScanElem<P>& e) {
+    double Vc[P], S = r;
+    for (int i = 0; i < P; i++) {
+        double s = 0.0;
+        for (int k = 0; k < P; k++) s = fma(sp.V[i][k], sp.prm.c[k], s);
+        Vc[i] = s;
+    }
+    for (int i = 0; i < P; i++) S = fma(sp.prm.c[i], Vc[i], S);
+    for (int i = 0; i < P; i++) {
+        for (int j = 0; j < P; j++) {
+            e.A[i][j] = 0.0;
+            e.J[i][j] = 0.0;
+            e.C[i][j] = sp.V[i][j] - Vc[i] * Vc[j] / S;
+        }
+        e.b[i] = Vc[i] * y / S;
+        e.eta[i] = 0.0;
+    }
+}
+
+// acc <- acc (x) a_k with a_k a single-point element: Sherman-Morrison, no inverse
+template <int P>
+__device__ void fold_step(const StepOps<P>& o, const double* c, double y, ScanElem<P>& a) {
+    double cw[P], aw[P];
+    double sp_ = o.S, wb = 0.0;
+    for (int i = 0; i < P; i++) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < P; k++) { s1 = fma(a.C[i][k], o.w[k], s1); s2 = fma(a.A[k][i], o.w[k], s2); }
+        cw[i] = s1;
+        aw[i] = s2;
+        wb = fma(o.w[i], a.b[i], wb);
+    }
+    for (int i = 0; i < P; i++) sp_ = fma(o.w[i], cw[i], sp_);
+    const double inv = 1.0 / sp_;
+    const double rr = (y - wb) * inv;
+    double bt[P], Ct[P][P], At[P][P];
+    for (int i = 0; i < P; i++) {
+        a.eta[i] = fma(aw[i], rr, a.eta[i]);
+        bt[i] = fma(cw[i], rr, a.b[i]);
+        for (int j = 0; j < P; j++) {
+            a.J[i][j] = fma(aw[i] * inv, aw[j], a.J[i][j]);
+            Ct[i][j] = fma(-cw[i] * inv, cw[j], a.C[i][j]);
+            At[i][j] = fma(-cw[i] * inv, aw[j], a.A[i][j]);
+        }
+    }
+    // G = (I - K c^T) F
+    double G[P][P];
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) G[i][j] = o.F[i][j] - o.K[i] * o.w[j];
+    double GC[P][P];
+    for (int i = 0; i < P; i++) {
+        double s = 0.0;
+        for (int k = 0; k < P; k++) s = fma(G[i][k], bt[k], s);
+        a.b[i] = fma(o.K[i], y, s);
+        for (int j = 0; j < P; j++) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int k = 0; k < P; k++) { s1 = fma(G[i][k], At[k][j], s1); s2 = fma(G[i][k], Ct[k][j], s2); }
+            a.A[i][j] = s1;
+            GC[i][j] = s2;
+        }
+    }
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) {
+            double s = 0.0;
+            for (int k = 0; k < P; k++) s = fma(GC[i][k], G[j][k], s);
+            a.C[i][j] = s + (o.Q[i][j] - o.K[i] * o.Qc[j]);
+        }
+    (void)c;
+}
+
+// Minv = (I + C J)^{-1} by Gauss-Jordan with partial pivoting; returns false if singular
+template <int P>
+__device__ bool inv_I_plus_CJ(const double C[P][P], const double J[P][P], double Minv[P][P]) {
+    double W[P][2 * P];
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) {
+            double s = (i == j) ? 1.0 : 0.0;
+            for (int k = 0; k < P; k++) s = fma(C[i][k], J[k][j], s);
+            W[i][j] = s;
+            W[i][P + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int col = 0; col < P; col++) {
+        int piv = col;
+        double best = fabs(W[col][col]);
+        for (int r = col + 1; r < P; r++)
+            if (fabs(W[r][col]) > best) { best = fabs(W[r][col]); piv = r; }
+        if (!(best > 0.0)) return false;
+        if (piv != col)
+            for (int j = 0; j < 2 * P; j++) { double t = W[col][j]; W[col][j] = W[piv][j]; W[piv][j] = t; }
+        double ip = 1.0 / W[col][col];
+        for (int j = 0; j < 2 * P; j++) W[col][j] *= ip;
+        for (int r = 0; r < P; r++)
+            if (r != col) {
+                double f = W[r][col];
+                for (int j = 0; j < 2 * P; j++) W[r][j] = fma(-f, W[col][j], W[r][j]);
+            }
+    }
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) Minv[i][j] = W[i][P + j];
+    return true;
+}
+
+// out = i (x) j (general operator).  out may alias neither input.
+template <int P>
+__device__ void combine(const ScanElem<P>& i, const ScanElem<P>& j, ScanElem<P>& out) {
+    double M[P][P];
+    inv_I_plus_CJ<P>(i.C, j.J, M);
+    double AM[P][P];  // A_j M
+    for (int r = 0; r < P; r++)
+        for (int c = 0; c < P; c++) {
+            double s = 0.0;
+            for (int k = 0; k < P; k++) s = fma(j.A[r][k], M[k][c], s);
+            AM[r][c] = s;
+        }
+    double v[P], u[P];
+    for (int r = 0; r < P; r++) {
+        double s = i.b[r], t = j.eta[r];
+        for (int k = 0; k < P; k++) { s = fma(i.C[r][k], j.eta[k], s); t = fma(-j.J[r][k], i.b[k], t); }
+        v[r] = s;   // b_i + C_i eta_j
+        u[r] = t;   // eta_j - J_j b_i
+    }
+    double AMC[P][P], MtJ[P][P], Mtu[P];
+    for (int r = 0; r < P; r++) {
+        double s = j.b[r], t = 0.0;
+        for (int k = 0; k < P; k++) { s = fma(AM[r][k], v[k], s); t = fma(M[k][r], u[k], t); }
+        out.b[r] = s;
+        Mtu[r] = t;
+        for (int c = 0; c < P; c++) {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int k = 0; k < P; k++) {
+                s1 = fma(AM[r][k], i.A[k][c], s1);
+                s2 = fma(AM[r][k], i.C[k][c], s2);
+                s3 = fma(M[k][r], j.J[k][c], s3);
+            }
+            out.A[r][c] = s1;
+            AMC[r][c] = s2;
+            MtJ[r][c] = s3;
+        }
+    }
+    double MtJA[P][P];
+    for (int r = 0; r < P; r++)
+        for (int c = 0; c < P; c++) {
+            double s1 = j.C[r][c], s2 = 0.0;
+            for (int k = 0; k < P; k++) { s1 = fma(AMC[r][k], j.A[c][k], s1); s2 = fma(MtJ[r][k], i.A[k][c], s2); }
+            out.C[r][c] = s1;
+            MtJA[r][c] = s2;
+        }
+    for (int r = 0; r < P; r++) {
+        double s = i.eta[r];
+        for (int k = 0; k < P; k++) s = fma(i.A[k][r], Mtu[k], s);
+        out.eta[r] = s;
+        for (int c = 0; c < P; c++) {
+            double t = i.J[r][c];
+            for (int k = 0; k < P; k++) t = fma(i.A[k][r], MtJA[k][c], t);
+            out.J[r][c] = t;
+        }
+    }
+}
+
+// filtered state (b, C) pushed through aggregate j
+template <int P>
+__device__ void apply_elem(FiltState<P>& f, const ScanElem<P>& j) {
+    double M[P][P];
+    inv_I_plus_CJ<P>(f.C, j.J, M);
+    double AM[P][P], v[P];
+    for (int r = 0; r < P; r++) {
+        double s = f.b[r];
+        for (int k = 0; k < P; k++) s = fma(f.C[r][k], j.eta[k], s);
+        v[r] = s;
+        for (int c = 0; c < P; c++) {
+            double t = 0.0;
+            for (int k = 0; k < P; k++) t = fma(j.A[r][k], M[k][c], t);
+            AM[r][c] = t;
+        }
+    }
+    double AMC[P][P], nb[P];
+    for (int r = 0; r < P; r++) {
+        double s = j.b[r];
+        for (int k = 0; k < P; k++) s = fma(AM[r][k], v[k], s);
+        nb[r] = s;
+        for (int c = 0; c < P; c++) {
+            double t = 0.0;
+            for (int k = 0; k < P; k++) t = fma(AM[r][k], f.C[k][c], t);
+            AMC[r][c] = t;
+        }
+    }
+    for (int r = 0; r < P; r++) {
+        f.b[r] = nb[r];
+        for (int c = 0; c < P; c++) {
+            double t = j.C[r][c];
+            for (int k = 0; k < P; k++) t = fma(AMC[r][k], j.A[c][k], t);
+            f.C[r][c] = t;
+        }
+    }
+}
+
+constexpr int SCAN_BLOCK = 128;
+
+// pass 1
+template <int P>
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_reduce_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
+                   ScanElem<P>* __restrict__ E) {
+    const int m = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (m >= nchunks || spp->status != TT_OK) return;
+    const ScanParams<P>& sp = *spp;
+    const int lo = m * chunk, hi = min(sv.ny, lo + chunk);
+    ScanElem<P> acc;
+    StepOps<P> o;
+    const double mu = sp.prm.mu, scale = sp.prm.scale;
+    if (lo == 0) {
+        first_elem<P>(sp, sv.y[0] - mu, scale * sv.e2_0, acc);
+    } else {
+        o.build(sp, sv.dt[lo - 1], scale * sv.e2n[lo - 1]);
+        single_elem<P>(sp, o, sv.y[lo] - mu, acc);
+    }
+    for (int k = lo + 1; k < hi; k++) {
+        o.build(sp, sv.dt[k - 1], scale * sv.e2n[k - 1]);
+        fold_step<P>(o, sp.prm.c, sv.y[k] - mu, acc);
+    }
+    E[m] = acc;
+}
+
+// pass 2: one block.  T threads, thread t owns aggregates [t*R, min((t+1)*R, M)).
+template <int P>
+__global__ void __launch_bounds__(256)
+scan_prefix_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ E, int M, int R, int T,
+                   ScanElem<P>* __restrict__ X /* 2*T */, FiltState<P>* __restrict__ F /* M */) {
+    if (spp->status != TT_OK) return;
+    const int t = threadIdx.x;
+    const int lo = t * R, hi = min(M, lo + R);
+    const bool have = t < T && lo < M;
+    if (have) {
+        ScanElem<P> acc = E[lo], tmp;
+        for (int m = lo + 1; m < hi; m++) {
+            combine<P>(acc, E[m], tmp);
+            acc = tmp;
+        }
+        X[t] = acc;
+    }
+    __syncthreads();
+    // Hillis-Steele inclusive scan over X[0..T), double buffered in global memory
+    int src = 0;
+    for (int off = 1; off < T; off <<= 1) {
+        if (have) {
+            if (t >= off) {
+                ScanElem<P> out;
+                combine<P>(X[src * T + t - off], X[src * T + t], out);
+                X[(1 - src) * T + t] = out;
+            } else {
+                X[(1 - src) * T + t] = X[src * T + t];
+            }
+        }
+        src = 1 - src;
+        __threadfence_block();
+        __syncthreads();
+    }
+    if (have) {
+        FiltState<P> f;
+        int start = lo;
+        if (t == 0) {
+            // chunk 0 has no predecessor; the state in front of chunk 1 is the first aggregate itself
+            for (int i = 0; i < P; i++) { f.b[i] = E[0].b[i]; for (int j = 0; j < P; j++) f.C[i][j] = E[0].C[i][j]; }
+            start = 1;
+        } else {
+            const ScanElem<P>& pre = X[src * T + t - 1];  // inclusive prefix of everything before this run
+            for (int i = 0; i < P; i++) { f.b[i] = pre.b[i]; for (int j = 0; j < P; j++) f.C[i][j] = pre.C[i][j]; }
+        }
+        for (int m = start; m < hi; m++) {
+            F[m] = f;
+            if (m + 1 < hi) apply_elem<P>(f, E[m]);
+        }
+    }
+}
+
+// pass 3
+template <int P>
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
+                   const FiltState<P>* __restrict__ F, double* __restrict__ LL) {
+    const int m = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (m >= nchunks || spp->status != TT_OK) return;
+    const RealParams<P> prm = spp->prm;
+    const int lo = m * chunk, hi = min(sv.ny, lo + chunk);
+    KalmanReal<P> kf;
+    LogLikAcc acc;
+    acc.init();
+    if (m == 0) {
+        kf.reset(prm, sv.e2_0);
+    } else {
+        const FiltState<P>& f = F[m];
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            kf.z[i] = f.b[i];
+#pragma unroll
+            for (int j = i; j < P; j++) kf.D[KalmanReal<P>::idx(i, j)] = f.C[i][j] - spp->V[i][j];
+        }
+        kf.template predict_observe<false>(prm, sv.dt[lo - 1], sv.e2n[lo - 1]);
+    }
+    const int len = hi - lo;
+    // every point of the chunk is scored; the transition out of the last one belongs to the next chunk
+    filter_span_impl<P, false>(kf, acc, prm, sv.dt + lo, sv.y + lo, sv.e2n + lo, len, len - 1);
+    LL[m] = acc.value();
+}
+
+// pass 4: deterministic fixed-order sum by one block
+template <int P>
+__global__ void __launch_bounds__(256)
+scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict__ LL, int M, double* __restrict__ out) {
+    __shared__ double sh[256];
+    if (spp->status != TT_OK) {
+        if (threadIdx.x == 0) *out = -INFINITY;
+        return;
+    }
+    double s = 0.0;
+    for (int m = threadIdx.x; m < M; m += 256) s += LL[m];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0] + spp->prm.logprior;
+}
+
+template <int P>
+static int scan_one(carma_series* s, int kind, int q, unsigned flags, const carma_prior_t& prior, const double* d_theta,
+                    double* d_out, int chunk, cudaStream_t st) {
+    SeriesView sv = s->view();
+    const int d = model_dim(kind, P, q);
+    if (chunk <= 0) chunk = 128;
+    chunk = std::max(chunk, 2);
+    const int M = (sv.ny + chunk - 1) / chunk;
+    int T = std::min(256, M);
+    const int R = (M + T - 1) / T;
+    T = (M + R - 1) / R;
+    size_t bytes = 256 + sizeof(ScanParams<P>) + (size_t)M * sizeof(ScanElem<P>) + 2 * (size_t)T * sizeof(ScanElem<P>) +
+                   (size_t)M * sizeof(FiltState<P>) + (size_t)M * sizeof(double) + 1024;
+    if (!s->scratch_misc.reserve(bytes)) return CARMA_ERR_CUDA;
+    char* base = (char*)s->scratch_misc.p;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    ScanParams<P>* sp = (ScanParams<P>*)base;
+    size_t off = align(sizeof(ScanParams<P>));
+    ScanElem<P>* E = (ScanElem<P>*)(base + off); off += align((size_t)M * sizeof(ScanElem<P>));
+    ScanElem<P>* X = (ScanElem<P>*)(base + off); off += align(2 * (size_t)T * sizeof(ScanElem<P>));
+    FiltState<P>* F = (FiltState<P>*)(base + off); off += align((size_t)M * sizeof(FiltState<P>));
+    double* LL = (double*)(base + off);
+    scan_params_kernel<P><<<1, 32, 0, st>>>(kind, q, d, flags, prior, d_theta, sp);
+    unsigned grid = (unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    scan_reduce_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, E);
+    scan_prefix_kernel<P><<<1, 256, 0, st>>>(sp, E, M, R, T, X, F);
+    scan_filter_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL);
+    scan_sum_kernel<P><<<1, 256, 0, st>>>(sp, LL, M, d_out);
+    return cuda_ok(cudaGetLastError(), "scan kernels launch") ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+}  // namespace carma
+
+using namespace carma;
+
+extern "C" {
+
+int carma_loglik_scan_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                          const double* d_theta, double* d_logpost, unsigned flags, int chunk, void* stream) {
+    if (!s || !prior || (!d_theta && n) || (!d_logpost && n)) { set_error("carma_loglik_scan_dev: null argument"); return CARMA_ERR_ARG; }
+    if (kind < CARMA_KIND_CAR1 || kind > CARMA_KIND_ZCARMA || p < 1 || p > MAX_P || (kind == CARMA_KIND_CAR1 && p != 1) ||
+        (kind == CARMA_KIND_CARMA && !(q >= 0 && q < p))) {
+        set_error("carma_loglik_scan_dev: invalid (kind,p,q)");
+        return CARMA_ERR_ARG;
+    }
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    const size_t d = (size_t)model_dim(kind, p, q);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (size_t i = 0; i < n; i++) {
+        int rc;
+        const double* th = d_theta + i * d;
+        double* out = d_logpost + i;
+        switch (p) {
+            case 1: rc = scan_one<1>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 2: rc = scan_one<2>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 3: rc = scan_one<3>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 4: rc = scan_one<4>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 5: rc = scan_one<5>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 6: rc = scan_one<6>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 7: rc = scan_one<7>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            default: rc = CARMA_ERR_ARG;
+        }
+        if (rc) return rc;
+    }
+    return CARMA_OK;
+}
+
+int carma_loglik_scan(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                      const double* theta, double* logpost, unsigned flags, int chunk) {
+    if (!s || !prior || (!theta && n) || (!logpost && n)) { set_error("carma_loglik_scan: null argument"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    if (p < 1 || p > MAX_P) { set_error("carma_loglik_scan: invalid p"); return CARMA_ERR_ARG; }
+    size_t d = (size_t)model_dim(kind, p, q);
+    if (!s->scratch_in.reserve(n * d * sizeof(double)) || !s->scratch_out.reserve(n * sizeof(double))) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(s->scratch_in.p, theta, n * d * sizeof(double), cudaMemcpyHostToDevice), "H2D theta")) return CARMA_ERR_CUDA;
+    int rc = carma_loglik_scan_dev(s, kind, p, q, prior, n, (const double*)s->scratch_in.p, (double*)s->scratch_out.p, flags, chunk, 0);
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpy(logpost, s->scratch_out.p, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H logpost")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+}  // extern "C"

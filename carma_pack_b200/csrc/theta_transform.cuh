@@ -141,9 +141,11 @@ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
 // Returns TT_NEG_INF when the log-density is -inf (bounds violated / singular), else TT_OK.
 // __noinline__: the prologue (LU on a PxP complex matrix) gets its own register allocation, so it
 // cannot push spills into the time loop of the calling kernel.
-template <int P>
+// Vr (optional): packed upper triangle (row-major, P(P+1)/2) of the stationary covariance in the real
+// basis, V_r = T V T^H restricted to its real part, where z = T x.  Only the scan kernels need it.
+template <int P, bool WITH_V = false>
 __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
-                                            RealParams<P>& out) {
+                                            RealParams<P>& out, double* Vr = nullptr) {
     constexpr double PI = 3.14159265358979323846;
     const double ysigma = th[0], scale = th[1];
     out.scale = scale;
@@ -255,6 +257,7 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
     cxd h[P];
 #pragma unroll
     for (int i = 0; i < P; i++) h[i] = cx(0, 0);
+    cxd Vfull[WITH_V ? P : 1][WITH_V ? P : 1];  // only materialised for the scan kernels
 #pragma unroll
     for (int i = 0; i < P; i++) {
 #pragma unroll
@@ -263,7 +266,33 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
             cxd vij = cdiv_simple(num, w[i] + conj(w[j]));
             h[i] = h[i] + vij * conj(b[j]);
             if (j > i) h[j] = h[j] + conj(vij) * conj(b[i]);
+            if (WITH_V) { Vfull[i][j] = vij; Vfull[j][i] = conj(vij); }
         }
+    }
+    if (WITH_V) {
+        // z_m = sum_k T[m][k] x_k with at most two non-zeros per row:
+        //   conjugate pair (a, a+1): u = (x_a + x_{a+1})/2, v = (x_a - x_{a+1})/(2i); real root: z = x
+        int k0[P], k1[P];
+        cxd t0[P], t1[P];
+#pragma unroll
+        for (int m = 0; m < P; m++) {
+            int s = m >> 1;
+            bool is_c = (m < 2 * (P / 2)) && ((cmask >> s) & 1u);
+            if (is_c) {
+                k0[m] = 2 * s; k1[m] = 2 * s + 1;
+                if ((m & 1) == 0) { t0[m] = cx(0.5, 0.0); t1[m] = cx(0.5, 0.0); }
+                else { t0[m] = cx(0.0, -0.5); t1[m] = cx(0.0, 0.5); }
+            } else {
+                k0[m] = m; k1[m] = m; t0[m] = cx(1.0, 0.0); t1[m] = cx(0.0, 0.0);
+            }
+        }
+        int o = 0;
+        for (int m = 0; m < P; m++)
+            for (int n = m; n < P; n++) {
+                cxd acc = t0[m] * Vfull[k0[m]][k0[n]] * conj(t0[n]) + t0[m] * Vfull[k0[m]][k1[n]] * conj(t1[n]) +
+                          t1[m] * Vfull[k1[m]][k0[n]] * conj(t0[n]) + t1[m] * Vfull[k1[m]][k1[n]] * conj(t1[n]);
+                Vr[o++] = acc.re;
+            }
     }
     double v0 = 0.0;
 #pragma unroll

@@ -119,6 +119,15 @@ int carma_multi_loglik_dev(carma_multi_series_t m, int kind, int p, int q, const
 int carma_multi_loglik(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,
                        const double* theta, double* logpost, unsigned flags);
 
+/* ---- one very long light curve: temporally parallel (associative-scan) form of the same LogDensity ----
+ * Replaces the strictly sequential Filter() loop (src/include/kfilter.hpp:126-132) when there is a single
+ * series and few theta rows, i.e. no batch parallelism (BASELINE config 5, ny = 10^6).  Same value as
+ * carma_loglik_batch up to floating-point re-association.  chunk: points per thread (0 = default 128). */
+int carma_loglik_scan_dev(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                          const double* d_theta, double* d_logpost, unsigned flags, int chunk, void* stream);
+int carma_loglik_scan(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                      const double* theta, double* logpost, unsigned flags, int chunk);
+
 /* ---- explicit-parameter filter: KalmanFilterp / KalmanFilter1 ------------------------------
  * Replaces KalmanFilterp(t,y,yerr,sigsqr,omega,ma).Filter() + GetMean()/GetVar()
  * (src/include/kfilter.hpp:303-334, 116-117; src/kfilter.cpp:138-215).  omega_reim: p complex roots as

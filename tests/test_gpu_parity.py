@@ -315,6 +315,54 @@ def test_philox_bit_exact_and_tdist(C, O):
         assert abs(a - b) <= 1e-13 * max(1.0, abs(b))
 
 
+def test_scan_kalman_matches_sequential_and_oracle(C, O):
+    """K5 (associative-scan Kalman): same log-density as the sequential kernel and the oracle for every
+    chunking, model family and root type; 1e-9 relative on the total (hard part 8)."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(17)
+    t, y, e = synth.readme_series(1000, 5)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    opr = O.default_prior(t, y)
+    for kind_name, p, q in [("CARMA", 5, 3), ("CARMA", 3, 1), ("CARP", 2, 0), ("CARP", 4, 0), ("CARMA", 7, 2),
+                            ("CAR1", 1, 0), ("ZCARMA", 3, 0)]:
+        kind, okind = getattr(C, "KIND_" + kind_name), getattr(O, "KIND_" + kind_name)
+        if kind_name == "CAR1":
+            th = np.array([[y.std(), 1.0, y.mean(), np.log(0.05)], [y.std() * 2, 1.2, y.mean() + 1, np.log(0.3)]])
+        else:
+            th = synth.prior_draws(6, p, q, t, y, rng)
+            if kind_name == "ZCARMA":
+                th = np.hstack([th, rng.uniform(-2, 2, (6, 1))])
+            th[0, 3], th[0, 4] = np.log(0.02), np.log(0.9)          # overdamped pair: two real roots
+            th[1, 0] = -1.0                                          # outside the prior: -inf
+        seq = s.loglik(kind, p, q, th, prior=pr)
+        want = O.logdensity(okind, p, q, t, y, e, th, prior=opr)
+        for chunk in (2, 7, 128, 4096):
+            got = s.loglik_scan(kind, p, q, th, prior=pr, chunk=chunk)
+            assert np.array_equal(np.isfinite(got), np.isfinite(seq)), (kind_name, chunk)
+            fin = np.isfinite(seq)
+            assert np.all(got[~fin] == seq[~fin])
+            np.testing.assert_allclose(got[fin], seq[fin], rtol=1e-9, err_msg="%s chunk=%d vs sequential" % (kind_name, chunk))
+            assert_logpost_parity(got, want, O.logdensity(okind, p, q, t, y, e, th, prior=opr, long_double=True),
+                                  max_illcond_frac=0.5, what="scan %s chunk=%d" % (kind_name, chunk),
+                                  ulp_eval=lambda rows, k: O.logdensity(okind, p, q, t, y, e, ulp_shift(th[rows], k), prior=opr))
+    s.close()
+    # a long series: 200,000 points, CARMA(3,1), against the CPU oracle
+    ar, ma, s2 = synth.carma31_truth()
+    n = 200000
+    tl = np.cumsum(rng.uniform(0.5, 1.5, n))
+    yl = rng.standard_normal(n)  # the likelihood of any data is a valid test; no need to simulate the process
+    el = np.full(n, 0.3)
+    sl = C.Series(tl, yl, el)
+    th = np.array([[1.0, 1.0, 0.0] + list(synth.roots_to_logquad(ar)) + [np.log(1.0 / 3.0)]])
+    got = sl.loglik_scan(C.KIND_CARMA, 3, 1, th, flags=C.IGNORE_BOUNDS)
+    seq = sl.loglik(C.KIND_CARMA, 3, 1, th, flags=C.IGNORE_BOUNDS)
+    want = O.logdensity(O.KIND_CARMA, 3, 1, tl, yl, el, th, ignore_prior=True)
+    assert abs(got[0] - seq[0]) <= 1e-9 * abs(seq[0])
+    assert abs(got[0] - want[0]) <= 1e-9 * abs(want[0])
+    sl.close()
+
+
 def test_fast_math_accuracy(C):
     """exp_fast / sincos_fast / rcp_fast (csrc/fast_math.cuh) against numpy in long double."""
     rng = np.random.default_rng(0)
