@@ -267,6 +267,82 @@ def run_ours(args, rank, world, local_rank):
               "finite_logposts": bool(torch.isfinite(dl).all().item())}
         sp.close()
 
+    # ---- survey-scale secondary metric (BASELINE config 5): one CARMA(3,1) theta per light curve, ny = 1000
+    survey = None
+    if not args.no_survey:
+        from carma_pack_b200 import synth
+        ncv, nyc = args.survey_curves, 1000
+        rng = np.random.default_rng(5000 + rank)
+        tt = np.cumsum(np.minimum(0.1 + np.abs(rng.standard_cauchy((ncv, nyc))), 1e3), axis=1).ravel()
+        yy = rng.standard_normal(ncv * nyc)   # throughput does not depend on the data values
+        ee = np.full(ncv * nyc, 0.3)
+        off = np.arange(ncv + 1, dtype=np.int64) * nyc
+        ms_ = C.MultiSeries(tt, yy, ee, off, device=dev)
+        ar31, _, _ = synth.carma31_truth()
+        th31 = np.tile(np.array([1.0, 1.0, 0.0] + list(synth.roots_to_logquad(ar31)) + [np.log(1.0 / 3.0)]), (ncv, 1))
+        th31[:, 3:] += 0.05 * rng.standard_normal((ncv, 4))
+        d_pr = torch.from_numpy(ms_.default_priors().view(np.float64).reshape(ncv, 6)).cuda()
+        d_th = torch.from_numpy(th31).cuda()
+        d_o = torch.empty(ncv, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
+        torch.cuda.synchronize()
+        reps = 5
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a.record()
+            ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        sv_ms = tot / reps
+        if dist:
+            tt_ = torch.tensor([sv_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            sv_ms = float(tt_.item())
+        survey = {"metric": "multi light-curve LogDensity, CARMA(3,1), ny=1000, one theta per curve",
+                  "value": world * ncv / (sv_ms * 1e-3), "unit": "curves/s", "curves_per_gpu": ncv, "ms": sv_ms,
+                  "hbm_gbs_algorithmic": ncv * nyc * 24 / (sv_ms * 1e-3) / 1e9,
+                  "tflops_algorithmic": ncv * f_eval(3, nyc) / (sv_ms * 1e-3) / 1e12,
+                  "finite": float(torch.isfinite(d_o).float().mean().item()),
+                  "data": "synthetic: Cauchy-gap times (generate_test_data.py:17), white-noise values"}
+        ms_.close()
+        del d_pr, d_th, d_o
+
+    # ---- single very long series through the associative-scan kernel (BASELINE config 5, ny = 10^6)
+    scan = None
+    if not args.no_scan and rank == 0:
+        from carma_pack_b200 import synth
+        nl = args.scan_ny
+        rng = np.random.default_rng(77)
+        tl = np.cumsum(rng.uniform(0.5, 1.5, nl))
+        sl = C.Series(tl, rng.standard_normal(nl), np.full(nl, 0.3), device=dev)
+        ar31, _, _ = synth.carma31_truth()
+        th1 = torch.tensor([[1.0, 1.0, 0.0] + list(synth.roots_to_logquad(ar31)) + [np.log(1.0 / 3.0)]], dtype=torch.float64).cuda()
+        o1 = torch.empty(1, dtype=torch.float64, device="cuda")
+        o2 = torch.empty(1, dtype=torch.float64, device="cuda")
+        prl = sl.default_prior()
+        sl.loglik_scan_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o1.data_ptr(), 1, prl, C.IGNORE_BOUNDS, 0, stream)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            sl.loglik_scan_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o1.data_ptr(), 1, prl, C.IGNORE_BOUNDS, 0, stream)
+        b.record()
+        torch.cuda.synchronize()
+        scan_ms = a.elapsed_time(b) / 5
+        a.record()
+        sl.loglik_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o2.data_ptr(), 1, prl, C.IGNORE_BOUNDS, stream)
+        b.record()
+        torch.cuda.synchronize()
+        seq_ms = a.elapsed_time(b)
+        scan = {"metric": "one CARMA(3,1) LogDensity on a single ny=%d series, associative-scan kernels (5 launches)" % nl,
+                "ms": scan_ms, "points_per_s": nl / (scan_ms * 1e-3), "sequential_one_thread_ms": seq_ms,
+                "rel_diff_vs_sequential": abs(float(o1.item()) - float(o2.item())) / abs(float(o2.item()))}
+        sl.close()
+
     # ---- NCCL: gather per-rank summaries only (no data-path collective)
     summary = [float(torch.nan_to_num(d_out, neginf=-1e300).max().item()), float(torch.isfinite(d_out).sum().item())]
     if dist:
@@ -318,6 +394,8 @@ def run_ours(args, rank, world, local_rank):
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
             "cpu_baseline": cpu,
             "pt_mcmc": pt,
+            "survey": survey,
+            "scan": scan,
             "summary": {"max_logpost": summary[0], "finite_rows": summary[1], "checksum_rank0": checksum},
         }
         print(json.dumps(line))
@@ -334,6 +412,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pt", action="store_true", help="skip the PT-MCMC secondary measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU baseline")
+    ap.add_argument("--no-survey", action="store_true", help="skip the multi light-curve secondary measurement")
+    ap.add_argument("--no-scan", action="store_true", help="skip the ny=1e6 associative-scan measurement")
+    ap.add_argument("--survey-curves", type=int, default=65536)
+    ap.add_argument("--scan-ny", type=int, default=1000000)
     ap.add_argument("--pt-ensembles", type=int, default=4096)
     ap.add_argument("--pt-iters", type=int, default=100)
     args = ap.parse_args()

@@ -235,8 +235,12 @@ class CarmaModel(object):
                              all_x=x, all_fun=f)
         return mle
 
-    def choose_order(self, pmax, qmax=None, pqlist=None, njobs=1, ntrials=100, seed=None, verbose=True):
-        """Choose (p,q) by minimising AICc over a grid of MLEs (carma_pack.py:131-192)."""
+    def choose_order(self, pmax, qmax=None, pqlist=None, njobs=1, ntrials=100, seed=None, verbose=True, dist=None):
+        """Choose (p,q) by minimising AICc over a grid of MLEs (carma_pack.py:131-192).
+
+        dist: an initialised torch.distributed module (one process per GPU).  The (p,q) models are then
+        partitioned over the ranks by cost (sharding.partition_weighted) and only the per-model summaries
+        (AICc, -loglik, theta-hat) are all-gathered; every rank returns the same result."""
         if not pmax > 0:
             raise ValueError("Order of AR polynomial must be at least 1.")
         if qmax is None:
@@ -245,9 +249,33 @@ class CarmaModel(object):
             raise ValueError("Order of AR polynomial, p, must be larger than order of MA polynimial, q.")
         if pqlist is None:
             pqlist = [(p, q) for p in range(1, pmax + 1) for q in range(min(p, qmax + 1))]
-        MLEs = []
-        for k, (p, q) in enumerate(pqlist):
-            MLEs.append(self.get_mle(p, q, ntrials=ntrials, njobs=njobs, seed=None if seed is None else seed + k))
+        mine = range(len(pqlist))
+        world = 1
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            from . import sharding
+            world = dist.get_world_size()
+            costs = [(20 * p * p + 36 * p + 7) * (4 + p + q) for p, q in pqlist]
+            mine = list(sharding.partition_weighted(costs, world, dist.get_rank()))
+        local = {}
+        for k in mine:
+            p, q = pqlist[k]
+            local[k] = self.get_mle(p, q, ntrials=ntrials, njobs=njobs, seed=None if seed is None else seed + k)
+        if world > 1:
+            from . import sharding
+            dmax = max(3 + p + q for p, q in pqlist)
+            table = np.full((len(pqlist), 2 + dmax), np.nan)
+            table[:, 0] = np.inf
+            for k, mle in local.items():
+                table[k, 0], table[k, 1] = mle.fun, mle.fun
+                table[k, 2:2 + len(mle.x)] = mle.x
+            best = sharding.best_aicc(table, dist)
+            MLEs = []
+            for k, (p, q) in enumerate(pqlist):
+                d = 4 if p == 1 else 3 + p + q
+                MLEs.append(OptimizeResult(x=best[k, 2:2 + d].copy(), fun=float(best[k, 1]),
+                                           success=bool(np.isfinite(best[k, 1])), message="gathered"))
+        else:
+            MLEs = [local[k] for k in range(len(pqlist))]
         best_AICc, AICc, best_MLE = 1e300, [], MLEs[0]
         if verbose:
             print("p, q, AICc:")
