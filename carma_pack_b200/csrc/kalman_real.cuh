@@ -132,15 +132,32 @@ struct KalmanReal {
         if (ODD) D[idx(P - 1, P - 1)] *= fo * fo;
 
         // ---- predicted observation: g = D c + h, var = c.g + e2, mean = c.z
-        double m = 0.0, vv = prm.scale * e2n;
+        // __dmul_rn: never contracted into the following add, so the all-conjugate-pairs loop and the
+        // generic loop round identically (results must not depend on which lanes share a warp)
+        double m = 0.0, vv = __dmul_rn(prm.scale, e2n);
+        if (ALLC) {
+            // c = (1,0, 1,0, ..., [1]): plain sums over the first component of every slot
 #pragma unroll
-        for (int i = 0; i < P; i++) {
-            double acc = prm.h[i];
+            for (int i = 0; i < P; i++) {
+                double acc = prm.h[i];
 #pragma unroll
-            for (int j = 0; j < P; j++) acc = fma(D[(i <= j) ? idx(i, j) : idx(j, i)], prm.c[j], acc);
-            g[i] = acc;
-            vv = fma(prm.c[i], acc, vv);
-            m = fma(prm.c[i], z[i], m);
+                for (int j = 0; j < P; j++)
+                    if ((j & 1) == 0) acc += D[(i <= j) ? idx(i, j) : idx(j, i)];
+                g[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                if ((i & 1) == 0) { vv += g[i]; m += z[i]; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                double acc = prm.h[i];
+#pragma unroll
+                for (int j = 0; j < P; j++) acc = fma(D[(i <= j) ? idx(i, j) : idx(j, i)], prm.c[j], acc);
+                g[i] = acc;
+                vv = fma(prm.c[i], acc, vv);
+                m = fma(prm.c[i], z[i], m);
+            }
         }
         var = vv;
         mean = m;

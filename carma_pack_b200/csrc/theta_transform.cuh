@@ -19,6 +19,8 @@
 // only p(p+1)/2 independent real numbers.  We carry z = (Re x_{2s}, Im x_{2s}) for a conjugate pair,
 // (x_{2s}, x_{2s+1}) for a real pair, and x_{p-1} for the odd root; the observation row b becomes
 // the real row c, and Cov(z, y) under the stationary law becomes the real vector h = V b^H.
+// (The components are additionally rescaled by their MA coefficient so that c is a 0/1 row: see the
+// "real half" block at the end of transform_theta.)
 #pragma once
 #include "../../include/carma_b200.h"
 #include "device_math.cuh"
@@ -279,11 +281,13 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
             int s = m >> 1;
             bool is_c = (m < 2 * (P / 2)) && ((cmask >> s) & 1u);
             if (is_c) {
+                // x^_a = s x_a, s = 2 b_a:  u^ = (s x_a + conj(s) x_a')/2,  v^ = (s x_a - conj(s) x_a')/(2i)
                 k0[m] = 2 * s; k1[m] = 2 * s + 1;
-                if ((m & 1) == 0) { t0[m] = cx(0.5, 0.0); t1[m] = cx(0.5, 0.0); }
-                else { t0[m] = cx(0.0, -0.5); t1[m] = cx(0.0, 0.5); }
+                cxd sc = 2.0 * b[2 * s];
+                if ((m & 1) == 0) { t0[m] = 0.5 * sc; t1[m] = 0.5 * conj(sc); }
+                else { t0[m] = cx(0.0, -0.5) * sc; t1[m] = cx(0.0, 0.5) * conj(sc); }
             } else {
-                k0[m] = m; k1[m] = m; t0[m] = cx(1.0, 0.0); t1[m] = cx(0.0, 0.0);
+                k0[m] = m; k1[m] = m; t0[m] = cx(b[m].re, 0.0); t1[m] = cx(0.0, 0.0);
             }
         }
         int o = 0;
@@ -299,33 +303,40 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
     for (int i = 0; i < P; i++) v0 += b[i].re * h[i].re - b[i].im * h[i].im;
     out.v0 = v0;
 
-    // ---- real half
+    // ---- real half, in the observation-normalised basis.  Each rotated component is rescaled by its own
+    // MA coefficient, x^_k = s_k x_k with s = 2 b (conjugate pair) or b (real root); the scaling commutes
+    // with the diagonal transition, and the observation becomes y = sum of the FIRST component of every
+    // slot (+ both components of a real pair): the row c only holds 0/1 and the time loop needs no
+    // multiplications by b.
 #pragma unroll
     for (int s = 0; s < P / 2; s++) {
         if ((cmask >> s) & 1u) {
             out.lam[2 * s] = w[2 * s].re;
             out.lam[2 * s + 1] = w[2 * s].im;
-            out.c[2 * s] = 2.0 * b[2 * s].re;
-            out.c[2 * s + 1] = -2.0 * b[2 * s].im;
+            out.c[2 * s] = 1.0;
+            out.c[2 * s + 1] = 0.0;
             // h restricted to the conjugate-symmetric subspace: (h_{2s} + conj(h_{2s+1})) / 2.  The LU
             // solution J is not exactly conjugate-symmetric (its error is cond(E) eps, consistent across
             // components); averaging keeps c.h == Re(b V b^H) to rounding, which is what the reference's
             // full complex recursion sees to first order in that asymmetry.
-            out.h[2 * s] = 0.5 * (h[2 * s].re + h[2 * s + 1].re);
-            out.h[2 * s + 1] = 0.5 * (h[2 * s].im - h[2 * s + 1].im);
+            cxd hs = cx(0.5 * (h[2 * s].re + h[2 * s + 1].re), 0.5 * (h[2 * s].im - h[2 * s + 1].im));
+            cxd sc = 2.0 * b[2 * s];
+            cxd hh = sc * hs;
+            out.h[2 * s] = hh.re;
+            out.h[2 * s + 1] = hh.im;
         } else {
             out.lam[2 * s] = w[2 * s].re;
             out.lam[2 * s + 1] = w[2 * s + 1].re;
-            out.c[2 * s] = b[2 * s].re;
-            out.c[2 * s + 1] = b[2 * s + 1].re;
-            out.h[2 * s] = h[2 * s].re;
-            out.h[2 * s + 1] = h[2 * s + 1].re;
+            out.c[2 * s] = 1.0;
+            out.c[2 * s + 1] = 1.0;
+            out.h[2 * s] = b[2 * s].re * h[2 * s].re;
+            out.h[2 * s + 1] = b[2 * s + 1].re * h[2 * s + 1].re;
         }
     }
     if (P & 1) {
         out.lam[P - 1] = w[P - 1].re;
-        out.c[P - 1] = b[P - 1].re;
-        out.h[P - 1] = h[P - 1].re;
+        out.c[P - 1] = 1.0;
+        out.h[P - 1] = b[P - 1].re * h[P - 1].re;
     }
 
     // ---- log prior (carpack.hpp:118-126, 444-456)
