@@ -196,34 +196,54 @@ struct LogLikAcc {
 
 // Run the recursion over `len` staged points (dt, y, next-point yerr^2); the last `len - nadv`
 // (0 or 1) points are only scored, not advanced past (end of the light curve).
-template <int P, bool ALLC>
+// PF = true: the three operands of step i+1 are loaded while step i is computed (software prefetch);
+// used when the series is read straight from global memory (K4, K5), pointless for shared memory.
+template <int P, bool ALLC, bool PF = false>
 __device__ __forceinline__ void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
                                                  const double* __restrict__ sdt, const double* __restrict__ sy,
                                                  const double* __restrict__ se, int len, int nadv) {
+    double y_c = 0.0, dt_c = 0.0, e_c = 0.0;
+    if (PF && len > 0) { y_c = sy[0]; dt_c = sdt[0]; e_c = se[0]; }
     for (int i = 0; i < nadv; i++) {
-        double innov = (sy[i] - prm.mu) - kf.mean;
+        double y_i, dt_i, e_i;
+        if (PF) {
+            y_i = y_c; dt_i = dt_c; e_i = e_c;
+            const int j = i + 1;  // j <= nadv <= len - 1 whenever the last point is only scored
+            if (j < len) { y_c = sy[j]; if (j < nadv) { dt_c = sdt[j]; e_c = se[j]; } }
+        } else {
+            y_i = sy[i]; dt_i = sdt[i]; e_i = se[i];
+        }
+        double innov = (y_i - prm.mu) - kf.mean;
         double inv = rcp_fast(kf.var);
         acc.add(kf.var, innov, inv);
-        kf.template advance<ALLC>(prm, innov, inv, sdt[i], se[i]);
+        kf.template advance<ALLC>(prm, innov, inv, dt_i, e_i);
     }
     if (nadv < len) {
-        double innov = (sy[len - 1] - prm.mu) - kf.mean;
+        double y_l = PF ? y_c : sy[len - 1];
+        double innov = (y_l - prm.mu) - kf.mean;
         double inv = rcp_fast(kf.var);
         acc.add(kf.var, innov, inv);
     }
+}
+
+template <int P, bool PF>
+__device__ __forceinline__ void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
+                                                const double* __restrict__ sdt, const double* __restrict__ sy,
+                                                const double* __restrict__ se, int len, int nadv) {
+    constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
+    // Warp-uniform choice: the straight-line all-conjugate-pairs loop only when EVERY active lane of the
+    // warp qualifies; otherwise all lanes run the generic loop (per-slot selection, reconverging each
+    // slot).  A per-lane choice would execute both loops back to back in a mixed warp.
+    const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
+    if (all_c) filter_span_impl<P, true, PF>(kf, acc, prm, sdt, sy, se, len, nadv);
+    else filter_span_impl<P, false, PF>(kf, acc, prm, sdt, sy, se, len, nadv);
 }
 
 template <int P>
 __device__ __forceinline__ void filter_span(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
                                             const double* __restrict__ sdt, const double* __restrict__ sy,
                                             const double* __restrict__ se, int len, int nadv) {
-    constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
-    // Warp-uniform choice: the straight-line all-conjugate-pairs loop only when EVERY active lane of the
-    // warp qualifies; otherwise all lanes run the generic loop (per-slot selection, reconverging each
-    // slot).  A per-lane choice would execute both loops back to back in a mixed warp.
-    const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
-    if (all_c) filter_span_impl<P, true>(kf, acc, prm, sdt, sy, se, len, nadv);
-    else filter_span_impl<P, false>(kf, acc, prm, sdt, sy, se, len, nadv);
+    filter_span_any<P, false>(kf, acc, prm, sdt, sy, se, len, nadv);
 }
 
 }  // namespace carma

@@ -164,7 +164,7 @@ multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y,
     kf.reset(prm, e2[o0]);
     acc.init();
     // e2 of the NEXT point is needed at step i: pass the array shifted by one
-    filter_span<P>(kf, acc, prm, dt + o0, y + o0, e2 + o0 + 1, ny, ny - 1);
+    filter_span_any<P, true>(kf, acc, prm, dt + o0, y + o0, e2 + o0 + 1, ny, ny - 1);
     out[c] = acc.value() + prm.logprior;
 }
 

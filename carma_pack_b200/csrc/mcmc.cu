@@ -165,7 +165,10 @@ __device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double
 __device__ __forceinline__ int tri(int k, int j) { return j * (j + 1) / 2 + k; }  // k <= j
 
 template <int P>
-__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 7 : (P == 6 ? 5 : 4))) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
+// min blocks/SM = 5 (<= 204 registers): the filter loop then keeps its whole state in registers (ncu r01d:
+// with a 128-register cap the loop spilled 3 loads + 2 stores per step and stalled on them), and
+// 5 x 148 = 740 resident blocks still hold BASELINE config 3 (683 blocks) in a single wave.
+__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 

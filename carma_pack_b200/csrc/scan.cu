@@ -429,7 +429,7 @@ scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chu
     }
     const int len = hi - lo;
     // every point of the chunk is scored; the transition out of the last one belongs to the next chunk
-    filter_span_impl<P, false>(kf, acc, prm, sv.dt + lo, sv.y + lo, sv.e2n + lo, len, len - 1);
+    filter_span_impl<P, false, true>(kf, acc, prm, sv.dt + lo, sv.y + lo, sv.e2n + lo, len, len - 1);
     LL[m] = acc.value();
 }
 
