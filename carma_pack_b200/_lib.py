@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
-    "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev",
+    "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
     "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
 ]
 
@@ -96,6 +96,8 @@ def _load():
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.carma_pt_run_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.POINTER(PTOpts), _sz,
                                    _vp, _vp, _vp, _vp, _vp, _vp]
+    L.carma_multi_pt_run.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(PTOpts), _sz,
+                                     _vp, _vp, _vp, _vp]
     L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
     L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
     L.carma_fastmath_dev.argtypes = [_dp, _sz, _dp, _dp, _dp, _dp]
@@ -311,6 +313,27 @@ class MultiSeries:
         check(lib.carma_multi_loglik(self.handle, kind, p, q, pp, th.ctypes.data, out.ctypes.data, flags),
               "carma_multi_loglik")
         return out
+
+    def pt_run(self, kind, p, q, nsamples, burnin, thin=1, ntemps=10, n_ensembles=1, seed=1, ensemble_offset=0,
+               priors=None, order_mode=0):
+        """One PT-MCMC run per light curve (n_ensembles ensembles each), all curves in one launch."""
+        d = model_dim(kind, p, q)
+        o = PTOpts()
+        lib.carma_pt_default_opts(ctypes.byref(o))
+        o.nsamples, o.burnin, o.thin, o.ntemps = int(nsamples), int(burnin), int(thin), int(ntemps)
+        o.seed, o.ensemble_offset, o.order_mode = seed, ensemble_offset, order_mode
+        nc = self.ncurves
+        samples = np.empty((nc, n_ensembles, nsamples, d))
+        logposts = np.empty((nc, n_ensembles, nsamples))
+        acc = np.empty((nc, n_ensembles, ntemps))
+        xr = np.empty((nc, n_ensembles, ntemps))
+        pp = None
+        if priors is not None:
+            priors = np.ascontiguousarray(priors, dtype=PRIOR_DTYPE)
+            pp = priors.ctypes.data
+        check(lib.carma_multi_pt_run(self.handle, kind, p, q, pp, ctypes.byref(o), n_ensembles, samples.ctypes.data,
+                                     logposts.ctypes.data, acc.ctypes.data, xr.ctypes.data), "carma_multi_pt_run")
+        return dict(samples=samples, logposts=logposts, accept_rates=acc, exchange_rates=xr)
 
     def loglik_dev(self, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags=0, stream=0):
         check(lib.carma_multi_loglik_dev(self.handle, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags, stream),

@@ -510,6 +510,11 @@ int carma_multi_series_create(const double* time, const double* y, const double*
         SeriesStats st = compute_stats(time + o0, y + o0, o1 - o0);
         prior_from_stats(st, 1, &m->priors_pop[c]);
         prior_from_stats(st, 0, &m->priors_sample[c]);
+        CurveInfo ci;
+        ci.prior = m->priors_pop[c];
+        ci.y_mean = st.mean; ci.y_var_sample = st.var_sample; ci.y_var_pop = st.var_pop;
+        ci.median_dt = st.median_dt; ci.tspan = st.tmax - st.tmin;
+        m->info.push_back(ci);
     }
     bool ok = cuda_ok(cudaMalloc((void**)&m->d_dt, (total + 1) * sizeof(double)), "cudaMalloc(multi dt)") &&
               cuda_ok(cudaMalloc((void**)&m->d_y, (total + 1) * sizeof(double)), "cudaMalloc(multi y)") &&
@@ -531,7 +536,7 @@ int carma_multi_series_destroy(carma_multi_series_t m) {
     if (m->d_y) cudaFree(m->d_y);
     if (m->d_e2) cudaFree(m->d_e2);
     if (m->d_off) cudaFree(m->d_off);
-    m->scratch_in.release(); m->scratch_out.release(); m->scratch_pr.release();
+    m->scratch_in.release(); m->scratch_out.release(); m->scratch_pr.release(); m->scratch_misc.release();
     delete m;
     return CARMA_OK;
 }

@@ -65,6 +65,20 @@ struct PTParams {
     int* status;                       // !=0 : a chain found no finite starting value
 };
 
+// multi light-curve mode: every block works on ONE curve of a ragged batch (its own series, prior and
+// starting-value statistics); ensembles are numbered globally curve-major.
+struct PTMulti {
+    const double* dt;
+    const double* y;
+    const double* e2;
+    const long long* off;
+    const CurveInfo* info;
+    int blocks_per_curve;
+    int max_nyp;
+    int enabled;
+    unsigned long long ens_per_curve;
+};
+
 // ---- starting-value RNG (mirrors oracle StartRng draw for draw) ---------------------------------
 struct StartRng {
     unsigned long long seed;
@@ -168,41 +182,71 @@ template <int P>
 // min blocks/SM = 5 (<= 204 registers): the filter loop then keeps its whole state in registers (ncu r01d:
 // with a 128-register cap the loop spilled 3 loads + 2 stores per step and stalled on them), and
 // 5 x 148 = 740 resident blocks still hold BASELINE config 3 (683 blocks) in a single wave.
-__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesView sv, PTParams pp, size_t chol_stride) {
+__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride,
+                                                                        PTMulti mm) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 
+    PTParams pp = pp_in;
     const int tid = threadIdx.x;
     const int T = pp.T, d = pp.d;
     const int epb = PT_BLOCK / T;
     const int e_local = tid / T, i = tid % T;
-    const unsigned long long ens = (unsigned long long)blockIdx.x * epb + e_local;
-    const bool active = (e_local < epb) && (ens < pp.n_ens);
     const size_t gtid = (size_t)blockIdx.x * PT_BLOCK + tid;
+    unsigned long long ens;
+    bool active;
+    const int nyp = mm.enabled ? mm.max_nyp : sv.nyp;
 
-    // ---- stage the light curve once (TMA bulk copy), resident for the whole run
     double* sdt = smem;
-    double* sy = smem + sv.nyp;
-    double* se = smem + 2 * (size_t)sv.nyp;
-    double* xth = smem + 3 * (size_t)sv.nyp;            // [PT_BLOCK][d] exchange area
+    double* sy = smem + nyp;
+    double* se = smem + 2 * (size_t)nyp;
+    double* xth = smem + 3 * (size_t)nyp + 2;          // [PT_BLOCK][d] exchange area
     double* xlp = xth + (size_t)PT_BLOCK * d;           // [PT_BLOCK]
     double* xu = xlp + PT_BLOCK;                        // [PT_BLOCK] exchange uniforms
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        // pieces of at most 64 KiB keep every transaction count far below the mbarrier tx limit
-        const uint32_t total = (uint32_t)(3 * (size_t)sv.nyp * 8);
-        mbar_expect_tx(&bar, total);
-        const uint32_t piece = 1u << 16;
-        for (uint32_t o = 0; o < total; o += piece) {
-            uint32_t b = min(piece, total - o);
-            bulk_g2s((char*)smem + o, (const char*)sv.dt + o, b, &bar);
+    double e2_0;
+    if (mm.enabled) {
+        // ---- this block's curve: coalesced cooperative copy (ragged offsets are not 16-byte aligned,
+        // so no bulk copy here); se is the yerr^2 array shifted by one point
+        const int curve = blockIdx.x / mm.blocks_per_curve;
+        const unsigned long long e_in = (unsigned long long)(blockIdx.x % mm.blocks_per_curve) * epb + e_local;
+        active = (e_local < epb) && (e_in < mm.ens_per_curve);
+        ens = (unsigned long long)curve * mm.ens_per_curve + e_in;
+        const long long o0 = mm.off[curve];
+        const int ny = (int)(mm.off[curve + 1] - o0);
+        const CurveInfo ci = mm.info[curve];
+        pp.prior = ci.prior;
+        pp.y_mean = ci.y_mean; pp.y_var_sample = ci.y_var_sample; pp.y_var_pop = ci.y_var_pop;
+        pp.median_dt = ci.median_dt; pp.tspan = ci.tspan; pp.ny = ny;
+        for (int k = tid; k < ny; k += PT_BLOCK) {
+            sdt[k] = mm.dt[o0 + k];
+            sy[k] = mm.y[o0 + k];
+            se[k] = mm.e2[o0 + k];
         }
+        __syncthreads();
+        e2_0 = se[0];
+        se = se + 1;
+    } else {
+        ens = (unsigned long long)blockIdx.x * epb + e_local;
+        active = (e_local < epb) && (ens < pp.n_ens);
+        // ---- stage the light curve once (TMA bulk copy), resident for the whole run
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // pieces of at most 64 KiB keep every transaction count far below the mbarrier tx limit
+            const uint32_t total = (uint32_t)(3 * (size_t)sv.nyp * 8);
+            mbar_expect_tx(&bar, total);
+            const uint32_t piece = 1u << 16;
+            for (uint32_t o = 0; o < total; o += piece) {
+                uint32_t b = min(piece, total - o);
+                bulk_g2s((char*)smem + o, (const char*)sv.dt + o, b, &bar);
+            }
+        }
+        mbar_wait(&bar, 0);
+        e2_0 = sv.e2_0;
     }
-    mbar_wait(&bar, 0);
 
     const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + i);
     const double temp = (T > 1) ? exp(log(pp.tmax) * (double)i / (double)(T - 1)) : 1.0;  // carmcmc.cpp:92-95
@@ -228,13 +272,13 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         bool ok = false;
         if (pp.init) {
             for (int j = 0; j < d; j++) th[j] = pp.init[j];
-            lp = logdensity_resident<P>(pp, th, sdt, sy, se, sv.e2_0);
+            lp = logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
             ok = isfinite(lp);
         }
         if (!ok) {
             for (int a = 0; a < pp.max_start && !ok; a++) {
                 StartRng g{pp.seed, chain, (uint32_t)a, 0u};
-                lp = starting_value_attempt<P>(pp, g, th, sdt, sy, se, sv.e2_0);
+                lp = starting_value_attempt<P>(pp, g, th, sdt, sy, se, e2_0);
                 ok = isfinite(lp);
             }
         }
@@ -262,7 +306,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
                 nv[j] = th[j] + s;
             }
             for (int j = d; j < MAX_D; j++) nv[j] = 0.0;
-            const double lpn = logdensity_resident<P>(pp, nv, sdt, sy, se, sv.e2_0);
+            const double lpn = logdensity_resident<P>(pp, nv, sdt, sy, se, e2_0);
             // ---- Accept (steps.cpp:36-56)
             double alpha = (lpn - lp) / temp;
             double u = NAN;
@@ -389,17 +433,17 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
     }
 }
 
-static size_t pt_smem_bytes(const SeriesView& sv, int d) {
-    return (3 * (size_t)sv.nyp + (size_t)PT_BLOCK * d + 2 * PT_BLOCK) * sizeof(double);
+static size_t pt_smem_bytes(int nyp, int d) {
+    return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 2 * PT_BLOCK) * sizeof(double);
 }
 
 template <int P>
 static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t chol_stride, unsigned grid,
-                             cudaStream_t stream) {
-    size_t smem = pt_smem_bytes(sv, pp.d);
+                             cudaStream_t stream, const PTMulti& mm) {
+    size_t smem = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d);
     cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride);
+    pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
     return cudaGetLastError();
 }
 
@@ -446,49 +490,68 @@ static int pt_check(carma_series_t s, int kind, int p, int q, const carma_prior_
     return CARMA_OK;
 }
 
-// Fill PTParams, reserve the Cholesky scratch (owned by the series) and launch.  All pointers are
-// device pointers.  *d_status_out receives the address of the device status word.
-static int pt_launch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* o,
-                     size_t n_ensembles, const double* d_init, double* d_samples, double* d_logposts,
-                     double* d_accept_rates, double* d_exchange_rates, carma_pt_trace_rec_t* d_rt,
-                     carma_pt_trace_rec_t* d_xt, double* d_pr, cudaStream_t st, int** d_status_out) {
-    SeriesView sv = s->view();
+// Fill PTParams, reserve the Cholesky scratch (owned by the series object) and launch.  All pointers
+// are device pointers.  Exactly one of `s` / `m` is non-null.  *d_status_out receives the address of the
+// device status word.
+static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* d_info, int kind, int p, int q,
+                     const carma_prior_t* prior, const carma_pt_opts_t* o, size_t n_ensembles, const double* d_init,
+                     double* d_samples, double* d_logposts, double* d_accept_rates, double* d_exchange_rates,
+                     carma_pt_trace_rec_t* d_rt, carma_pt_trace_rec_t* d_xt, double* d_pr, cudaStream_t st,
+                     int** d_status_out) {
+    SeriesView sv{};
+    PTMulti mm{};
     PTParams pp{};
     pp.kind = kind; pp.q = q; pp.d = model_dim(kind, p, q);
-    pp.prior = *prior;
     pp.nsamples = o->nsamples; pp.burnin = o->burnin; pp.thin = o->thin; pp.T = o->ntemps;
     pp.total_iters = o->burnin + o->nsamples * o->thin;
     pp.tmax = o->tmax; pp.dof = o->dof; pp.target = o->target_rate; pp.gamma = o->gamma;
     pp.seed = o->seed; pp.ens_offset = o->ensemble_offset; pp.max_start = std::max(1, o->max_start_attempts);
     pp.order_mode = o->order_mode; pp.record = (d_rt && d_xt && d_pr) ? 1 : 0;
-    pp.n_ens = n_ensembles;
-    pp.y_mean = s->st.mean; pp.y_var_sample = s->st.var_sample; pp.y_var_pop = s->st.var_pop;
-    pp.median_dt = s->st.median_dt; pp.tspan = s->st.tmax - s->st.tmin; pp.ny = (int)s->ny;
     pp.init = d_init; pp.samples = d_samples; pp.logposts = d_logposts;
     pp.accept_rates = d_accept_rates; pp.exchange_rates = d_exchange_rates;
     pp.ram_trace = d_rt; pp.exch_trace = d_xt; pp.proposals = d_pr;
-    if (pt_smem_bytes(sv, pp.d) > 220 * 1024) {
+    const int epb = PT_BLOCK / pp.T;
+    unsigned grid;
+    DevBuf* scratch;
+    if (s) {
+        sv = s->view();
+        pp.prior = *prior;
+        pp.n_ens = n_ensembles;
+        pp.y_mean = s->st.mean; pp.y_var_sample = s->st.var_sample; pp.y_var_pop = s->st.var_pop;
+        pp.median_dt = s->st.median_dt; pp.tspan = s->st.tmax - s->st.tmin; pp.ny = (int)s->ny;
+        grid = (unsigned)((n_ensembles + epb - 1) / epb);
+        scratch = &s->scratch_misc;
+    } else {
+        // n_ensembles = ensembles PER CURVE
+        mm.enabled = 1;
+        mm.dt = m->d_dt; mm.y = m->d_y; mm.e2 = m->d_e2; mm.off = m->d_off; mm.info = d_info;
+        mm.blocks_per_curve = (int)((n_ensembles + epb - 1) / epb);
+        mm.max_nyp = (m->max_ny + 1) & ~1;
+        mm.ens_per_curve = n_ensembles;
+        pp.n_ens = n_ensembles * m->ncurves;
+        grid = (unsigned)(m->ncurves * (size_t)mm.blocks_per_curve);
+        scratch = &m->scratch_misc;
+    }
+    if (pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) > 220 * 1024) {
         set_error("carma_pt_run: series too long for the resident-series MCMC kernel (ny <= ~9000)");
         return CARMA_ERR_ARG;
     }
-    int epb = PT_BLOCK / pp.T;
-    unsigned grid = (unsigned)((n_ensembles + epb - 1) / epb);
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
-    if (!s->scratch_misc.reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;
-    pp.chol = (double*)s->scratch_misc.p;
-    pp.status = (int*)((char*)s->scratch_misc.p + ntri * nthreads * sizeof(double));
+    if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;
+    pp.chol = (double*)scratch->p;
+    pp.status = (int*)((char*)scratch->p + ntri * nthreads * sizeof(double));
     if (d_status_out) *d_status_out = pp.status;
     if (!cuda_ok(cudaMemsetAsync(pp.status, 0, sizeof(int), st), "memset status")) return CARMA_ERR_CUDA;
     cudaError_t e;
     switch (p) {
-        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st); break;
-        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st); break;
-        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st); break;
-        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st); break;
-        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st); break;
-        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st); break;
-        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st); break;
+        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st, mm); break;
+        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st, mm); break;
+        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st, mm); break;
+        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st, mm); break;
+        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st, mm); break;
+        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st, mm); break;
+        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st, mm); break;
         default: e = cudaErrorInvalidValue;
     }
     if (!cuda_ok(e, "pt_kernel launch")) return CARMA_ERR_CUDA;
@@ -502,8 +565,8 @@ int carma_pt_run_dev(carma_series_t s, int kind, int p, int q, const carma_prior
     if (rc) return rc;
     if (n_ensembles == 0) return CARMA_OK;
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
-    return pt_launch(s, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_logposts, d_accept_rates,
-                     d_exchange_rates, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr);
+    return pt_launch(s, nullptr, nullptr, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_logposts,
+                     d_accept_rates, d_exchange_rates, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, const carma_pt_opts_t* o,
@@ -536,8 +599,8 @@ int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* 
         d_init = (const double*)s->scratch_in.p;
     }
     int* d_status = nullptr;
-    rc = pt_launch(s, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_lp, d_ar, d_xr, rec ? d_rt : nullptr,
-                   rec ? d_xt : nullptr, rec ? d_pr : nullptr, 0, &d_status);
+    rc = pt_launch(s, nullptr, nullptr, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_lp, d_ar, d_xr,
+                   rec ? d_rt : nullptr, rec ? d_xt : nullptr, rec ? d_pr : nullptr, 0, &d_status);
     if (rc) return rc;
     if (!cuda_ok(cudaDeviceSynchronize(), "pt_kernel")) return CARMA_ERR_CUDA;
     int status = 0;
@@ -552,6 +615,46 @@ int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* 
              cuda_ok(cudaMemcpy(exch_trace, d_xt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost), "D2H exch trace") &&
              cuda_ok(cudaMemcpy(proposals, d_pr, n_tr * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H proposals");
     }
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+// One PT-MCMC run per light curve of a ragged batch (n_ensembles independent ensembles each), one launch.
+int carma_multi_pt_run(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,
+                       const carma_pt_opts_t* o, size_t n_ensembles, double* samples, double* logposts,
+                       double* accept_rates, double* exchange_rates) {
+    if (!m || !o || !samples || !logposts) { set_error("carma_multi_pt_run: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model_pt(kind, p, q)) { set_error("carma_multi_pt_run: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (o->ntemps < 1 || o->ntemps > PT_BLOCK || o->thin < 1 || o->nsamples < 0 || o->burnin < 0 || (o->dof & 1) || o->dof < 2) {
+        set_error("carma_multi_pt_run: invalid options (1 <= ntemps <= 64, thin >= 1, even dof >= 2)");
+        return CARMA_ERR_ARG;
+    }
+    if (n_ensembles == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(m->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    const size_t d = (size_t)model_dim(kind, p, q), T = (size_t)o->ntemps, nc = m->ncurves;
+    const size_t n_tot = nc * n_ensembles, n_s = n_tot * (size_t)o->nsamples;
+    std::vector<CurveInfo> info(m->info);
+    if (priors)
+        for (size_t c = 0; c < nc; c++) info[c].prior = priors[c];
+    size_t bytes_out = (n_s * d + n_s + 2 * n_tot * T) * sizeof(double);
+    if (!m->scratch_out.reserve(bytes_out + 64) || !m->scratch_pr.reserve(nc * sizeof(CurveInfo))) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpy(m->scratch_pr.p, info.data(), nc * sizeof(CurveInfo), cudaMemcpyHostToDevice), "H2D curve info")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemset(m->scratch_out.p, 0, bytes_out), "memset outputs")) return CARMA_ERR_CUDA;
+    double* d_samples = (double*)m->scratch_out.p;
+    double* d_lp = d_samples + n_s * d;
+    double* d_ar = d_lp + n_s;
+    double* d_xr = d_ar + n_tot * T;
+    int* d_status = nullptr;
+    int rc = pt_launch(nullptr, m, (const CurveInfo*)m->scratch_pr.p, kind, p, q, nullptr, o, n_ensembles, nullptr,
+                       d_samples, d_lp, d_ar, d_xr, nullptr, nullptr, nullptr, 0, &d_status);
+    if (rc) return rc;
+    if (!cuda_ok(cudaDeviceSynchronize(), "pt_kernel (multi)")) return CARMA_ERR_CUDA;
+    int status = 0;
+    if (!cuda_ok(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost), "D2H status")) return CARMA_ERR_CUDA;
+    if (status) { set_error("carma_multi_pt_run: a chain found no finite starting value within max_start_attempts"); return CARMA_ERR_START; }
+    bool ok = cuda_ok(cudaMemcpy(samples, d_samples, n_s * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H samples") &&
+              cuda_ok(cudaMemcpy(logposts, d_lp, n_s * sizeof(double), cudaMemcpyDeviceToHost), "D2H logposts");
+    if (ok && accept_rates) ok = cuda_ok(cudaMemcpy(accept_rates, d_ar, n_tot * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H accept");
+    if (ok && exchange_rates) ok = cuda_ok(cudaMemcpy(exchange_rates, d_xr, n_tot * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H exch");
     return ok ? CARMA_OK : CARMA_ERR_CUDA;
 }
 

@@ -49,6 +49,14 @@ struct carma_series {
     }
 };
 
+namespace carma {
+// per-curve constants needed by the on-device samplers (prior + starting-value statistics)
+struct CurveInfo {
+    carma_prior_t prior;
+    double y_mean, y_var_sample, y_var_pop, median_dt, tspan;
+};
+}  // namespace carma
+
 struct carma_multi_series {
     int device = 0;
     size_t ncurves = 0;
@@ -61,7 +69,8 @@ struct carma_multi_series {
     long long* d_off = nullptr;
     std::vector<long long> off;
     std::vector<carma_prior_t> priors_pop, priors_sample;
-    carma::DevBuf scratch_in, scratch_out, scratch_pr;
+    std::vector<carma::CurveInfo> info;  // default (population-variance) priors + statistics
+    carma::DevBuf scratch_in, scratch_out, scratch_pr, scratch_misc;
     int max_ny = 0;
 };
 

@@ -190,6 +190,16 @@ int carma_pt_run_dev(carma_series_t s, int kind, int p, int q, const carma_prior
                      const carma_pt_opts_t* opts, size_t n_ensembles, const double* d_init, double* d_samples,
                      double* d_logposts, double* d_accept_rates, double* d_exchange_rates, void* stream);
 
+/* One PT-MCMC run per light curve of a ragged batch, n_ensembles independent ensembles per curve, in ONE
+ * launch (every block stages its own curve).  The survey-scale form of RunCarmaSampler: the reference
+ * would loop over objects in Python.  priors: ncurves entries or NULL (population-variance defaults).
+ * Host outputs: samples[ncurves][n_ensembles][nsamples][d], logposts[ncurves][n_ensembles][nsamples],
+ * accept_rates / exchange_rates[ncurves][n_ensembles][ntemps] (may be NULL).  Chain ids of the Philox
+ * streams: ((ensemble_offset + curve*n_ensembles + e) * ntemps + temperature). */
+int carma_multi_pt_run(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,
+                       const carma_pt_opts_t* opts, size_t n_ensembles, double* samples, double* logposts,
+                       double* accept_rates, double* exchange_rates);
+
 /* ---- utilities ---------------------------------------------------------------------------- */
 /* Saturating FP64 FMA micro-benchmark on `device`: returns sustained DFMA TFLOP/s (2 flops per
  * FMA).  Used by bench.py as the measured FP64 roofline denominator. */

@@ -482,6 +482,33 @@ def test_pt_run_with_init_and_parallel_mode(C, O):
     s.close()
 
 
+def test_multi_series_pt_run_equals_per_curve_runs(C):
+    """Survey-scale MCMC: one launch over a ragged batch of light curves gives, for every curve, exactly the
+    chain of a single-series run with the matching global ensemble index."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(31)
+    ar, ma, s2 = synth.carma31_truth()
+    ts, ys, es, off = [], [], [], [0]
+    for c in range(5):
+        ny = int(rng.integers(40, 160))
+        t = np.cumsum(rng.uniform(0.5, 2.0, ny))
+        y = 3.0 + synth.carma_process(t, s2, ar, ma, rng) + 0.1 * rng.standard_normal(ny)
+        ts.append(t); ys.append(y); es.append(np.full(ny, 0.1)); off.append(off[-1] + ny)
+    m = C.MultiSeries(np.concatenate(ts), np.concatenate(ys), np.concatenate(es), off)
+    nens, T = 3, 4
+    res = m.pt_run(C.KIND_CARMA, 3, 1, 30, 40, ntemps=T, n_ensembles=nens, seed=77)
+    assert res["samples"].shape == (5, nens, 30, 7) and np.all(np.isfinite(res["logposts"]))
+    for c in (0, 2, 4):
+        s = C.Series(ts[c], ys[c], es[c])
+        one = s.pt_run(C.KIND_CARMA, 3, 1, 30, 40, ntemps=T, n_ensembles=nens, seed=77, ensemble_offset=c * nens,
+                       prior=s.default_prior())
+        assert np.array_equal(one["samples"], res["samples"][c])
+        assert np.array_equal(one["logposts"], res["logposts"][c])
+        assert np.array_equal(one["accept_rates"], res["accept_rates"][c])
+        s.close()
+    m.close()
+
+
 def test_pt_posterior_recovers_truth_car1(C):
     """Statistical check in the spirit of carma_unit_tests.cpp:1319-1375 (posterior within 3 sigma of truth),
     using many independent ensembles instead of one long chain."""
