@@ -386,7 +386,10 @@ def run_ours(args, rank, world, local_rank):
                     "matches_device_path": same},
             "gpu_launches": K,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                         "traffic": 63.8e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, "
+                         "ncu --set full, profiles/r01d_k1_ncu_key_metrics.csv (bytes; 6.3e6 algorithmic, the "
+                         "rest is the prologue's local-memory frame)",
                          "kernel": "loglik_batch_kernel<5>", "kernel_ms": kern_ms,
                          "flops_per_eval": fe, "flops_per_step_formula": "20p^2+36p+7 (SURVEY 8d), transcendentals excluded",
                          "peak_source": "DFMA saturation micro-benchmark run on this GPU in this process "
