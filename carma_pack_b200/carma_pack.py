@@ -204,9 +204,11 @@ class CarmaModel(object):
             hi += [np.inf] * q
         return np.array(lo), np.array(hi)
 
-    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200):
+    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0):
         """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
-        in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored."""
+        in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
+        global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
+        rank runs it)."""
         kind = _kind_for(p, q)
         d = model_dim(kind, p, q)
         if seed is None:
@@ -214,15 +216,15 @@ class CarmaModel(object):
         prior = self.series.default_prior(population_var=True)
         # initial guesses: nsamples=1, nburnin=25, nwalkers=10 MCMC runs (carma_pack.py:197-216)
         res = self.series.pt_run(kind, p, q, 1, 25, ntemps=1 if p == 1 else 10, n_ensembles=ntrials, seed=seed,
-                                 prior=prior)
+                                 ensemble_offset=trial_offset, prior=prior)
         x0 = res["samples"][:, 0, :].copy()
         x0[:, 1] = 1.0  # carma_pack.py:216
         lo, hi = self._mle_bounds(p, q)
-        rng = np.random.default_rng(seed)
-        for j in range(d):  # carma_pack.py:244-248
-            if np.isfinite(lo[j]):
-                out = (x0[:, j] < lo[j]) | (x0[:, j] > hi[j])
-                x0[out, j] = rng.uniform(lo[j], hi[j], out.sum())
+        for i in range(ntrials):  # carma_pack.py:244-248, one generator per global trial index
+            rng = np.random.default_rng([seed % (2 ** 63), trial_offset + i])
+            for j in range(d):
+                if np.isfinite(lo[j]) and ((x0[i, j] < lo[j]) or (x0[i, j] > hi[j])):
+                    x0[i, j] = rng.uniform(lo[j], hi[j])
         flags = 0 if p == 1 else IGNORE_BOUNDS  # SetMLE(True) only for p > 1 (carma_pack.py:242)
 
         def negloglik(th):
@@ -249,17 +251,24 @@ class CarmaModel(object):
             raise ValueError("Order of AR polynomial, p, must be larger than order of MA polynimial, q.")
         if pqlist is None:
             pqlist = [(p, q) for p in range(1, pmax + 1) for q in range(min(p, qmax + 1))]
-        mine = range(len(pqlist))
         world = 1
+        units = [(k, 0, ntrials) for k in range(len(pqlist))]   # (model, first trial, number of trials)
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
             from . import sharding
             world = dist.get_world_size()
-            costs = [(20 * p * p + 36 * p + 7) * (4 + p + q) for p, q in pqlist]
-            mine = list(sharding.partition_weighted(costs, world, dist.get_rank()))
+            # unit of work = one (model, trial); cost ~ F_step(p) (d+1); contiguous cost-weighted blocks
+            cost1 = [(20 * p * p + 36 * p + 7) * (4 + p + q) for p, q in pqlist]
+            costs = np.repeat(np.array(cost1, dtype=float), ntrials)
+            mine = sharding.partition_weighted(costs, world, dist.get_rank())
+            units = []
+            for k in sorted(set(int(u) // ntrials for u in mine)):
+                tr = [int(u) % ntrials for u in mine if int(u) // ntrials == k]
+                units.append((k, min(tr), len(tr)))
         local = {}
-        for k in mine:
+        for k, first, count in units:
             p, q = pqlist[k]
-            local[k] = self.get_mle(p, q, ntrials=ntrials, njobs=njobs, seed=None if seed is None else seed + k)
+            local[k] = self.get_mle(p, q, ntrials=count, njobs=njobs, seed=None if seed is None else seed + k,
+                                    trial_offset=first)
         if world > 1:
             from . import sharding
             dmax = max(3 + p + q for p, q in pqlist)
