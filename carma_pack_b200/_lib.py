@@ -19,7 +19,8 @@ MAX_P = 7
 EXPORTED_SYMBOLS = [
     "carma_last_error", "carma_abi_version", "carma_device_count",
     "carma_series_create", "carma_series_destroy", "carma_series_length", "carma_series_default_prior",
-    "carma_loglik_batch_dev", "carma_loglik_batch", "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
+    "carma_loglik_batch_dev", "carma_loglik_batch", "carma_loglik_batch_async", "carma_loglik_batch_wait",
+    "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
@@ -79,6 +80,9 @@ def _load():
                                         ctypes.c_uint, ctypes.c_int, _vp]
     L.carma_loglik_scan.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp, ctypes.c_uint,
                                     ctypes.c_int]
+    L.carma_loglik_batch_async.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, _sz, _vp, _vp,
+                                           ctypes.c_uint, ctypes.c_int]
+    L.carma_loglik_batch_wait.argtypes = [_vp, ctypes.c_int]
     L.carma_log_prior.argtypes = [ctypes.c_int, ctypes.c_int, _dp, pr, _dp]
     L.carma_multi_series_create.argtypes = [_dp, _dp, _dp, ctypes.POINTER(ctypes.c_int64), _sz, ctypes.c_int,
                                             ctypes.POINTER(_vp)]
@@ -180,6 +184,14 @@ class Series:
         check(lib.carma_loglik_batch(self.handle, kind, p, q, ctypes.byref(prior), th.shape[0],
                                      th.ctypes.data, out.ctypes.data, flags), "carma_loglik_batch")
         return out
+
+    def loglik_async(self, kind, p, q, theta_ptr, out_ptr, n, prior, slot, flags=0):
+        """Enqueue H2D + kernel + D2H for host buffers (raw addresses, ideally pinned) on pipeline slot 0/1."""
+        check(lib.carma_loglik_batch_async(self.handle, kind, p, q, ctypes.byref(prior), n, theta_ptr, out_ptr, flags,
+                                           slot), "carma_loglik_batch_async")
+
+    def loglik_wait(self, slot):
+        check(lib.carma_loglik_batch_wait(self.handle, slot), "carma_loglik_batch_wait")
 
     def loglik_scan(self, kind, p, q, theta, prior=None, flags=0, chunk=0):
         """Same value as loglik(), computed by the temporally parallel scan (for one very long series)."""

@@ -428,6 +428,10 @@ int carma_series_destroy(carma_series_t s) {
     cudaSetDevice(s->device);
     if (s->d_pack) cudaFree(s->d_pack);
     s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release();
+    for (int k = 0; k < 2; k++) {
+        s->slot_in[k].release(); s->slot_out[k].release();
+        if (s->slot_stream[k]) cudaStreamDestroy(s->slot_stream[k]);
+    }
     delete s;
     return CARMA_OK;
 }
@@ -469,6 +473,35 @@ int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_pri
     if (rc) return rc;
     if (!cuda_ok(cudaMemcpyAsync(logpost, s->scratch_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
     if (!cuda_ok(cudaStreamSynchronize(st), "loglik_batch sync")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                             const double* theta, double* logpost, unsigned flags, int slot) {
+    if (!s || !prior || (!theta && n) || (!logpost && n) || slot < 0 || slot > 1) { set_error("carma_loglik_batch_async: bad argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_loglik_batch_async: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    if (!s->slot_stream[slot] && !cuda_ok(cudaStreamCreateWithFlags(&s->slot_stream[slot], cudaStreamNonBlocking), "cudaStreamCreate")) return CARMA_ERR_CUDA;
+    cudaStream_t st = s->slot_stream[slot];
+    size_t d = (size_t)model_dim(kind, p, q);
+    // growing a slot buffer must not race with work still queued on that slot
+    if (n * d * sizeof(double) > s->slot_in[slot].cap || n * sizeof(double) > s->slot_out[slot].cap) {
+        if (!cuda_ok(cudaStreamSynchronize(st), "slot sync")) return CARMA_ERR_CUDA;
+        if (!s->slot_in[slot].reserve(n * d * sizeof(double)) || !s->slot_out[slot].reserve(n * sizeof(double))) return CARMA_ERR_CUDA;
+    }
+    if (!cuda_ok(cudaMemcpyAsync(s->slot_in[slot].p, theta, n * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
+    int rc = carma_loglik_batch_dev(s, kind, p, q, prior, n, (const double*)s->slot_in[slot].p, (double*)s->slot_out[slot].p, flags, st);
+    if (rc) return rc;
+    if (!cuda_ok(cudaMemcpyAsync(logpost, s->slot_out[slot].p, n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_loglik_batch_wait(carma_series_t s, int slot) {
+    if (!s || slot < 0 || slot > 1) { set_error("carma_loglik_batch_wait: bad argument"); return CARMA_ERR_ARG; }
+    if (!s->slot_stream[slot]) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaStreamSynchronize(s->slot_stream[slot]), "loglik_batch_wait")) return CARMA_ERR_CUDA;
     return CARMA_OK;
 }
 

@@ -36,6 +36,9 @@ struct carma_series {
     std::vector<double> t, y, yerr;
     carma::SeriesStats st{};
     carma::DevBuf scratch_in, scratch_out, scratch_misc;
+    // two pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
+    carma::DevBuf slot_in[2], slot_out[2];
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
     carma::SeriesView view() const {
         carma::SeriesView v;
         v.dt = d_pack;

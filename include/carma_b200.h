@@ -104,6 +104,14 @@ int carma_loglik_batch_dev(carma_series_t s, int kind, int p, int q, const carma
                            const double* d_theta, double* d_logpost, unsigned flags, void* stream);
 int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
                        const double* theta, double* logpost, unsigned flags);
+/* Pipelined form of carma_loglik_batch for callers that evaluate batch after batch from host memory
+ * (optimisers, samplers driven from the host): enqueue H2D + kernel + D2H on one of two internal slots
+ * (slot = 0 or 1, each with its own stream and device buffers) and return at once; the copies of one slot
+ * overlap the kernel of the other.  The host buffers must stay valid (and should be pinned) until
+ * carma_loglik_batch_wait(s, slot) returns. */
+int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
+                             const double* theta, double* logpost, unsigned flags, int slot);
+int carma_loglik_batch_wait(carma_series_t s, int slot);
 /* CARMA_Base::getLogPrior (src/include/carpack.hpp:221-225): host-side scalar helper. */
 int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out);
 

@@ -252,6 +252,26 @@ def test_loglik_long_series_chunked_pipeline(C, O, kelly):
     s1.close(); s2.close()
 
 
+def test_async_pipeline_equals_blocking_call(C):
+    """carma_loglik_batch_async/_wait (two slots) returns exactly what the blocking call returns."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(270, 3)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    batches = [np.ascontiguousarray(synth.theta_batch(4096 + 512 * k, t, y, seed=k)) for k in range(5)]
+    want = [s.loglik(C.KIND_CARMA, 5, 3, b, prior=pr) for b in batches]
+    outs = [np.empty(b.shape[0]) for b in batches]
+    for k, b in enumerate(batches):
+        slot = k & 1
+        if k >= 2:
+            s.loglik_wait(slot)
+        s.loglik_async(C.KIND_CARMA, 5, 3, b.ctypes.data, outs[k].ctypes.data, b.shape[0], pr, slot)
+    s.loglik_wait(0); s.loglik_wait(1)
+    for k in range(5):
+        assert np.array_equal(outs[k], want[k], equal_nan=True)
+    s.close()
+
+
 def test_scaling_property(C):
     """Size-independent property: (y, yerr, sigma_y, mu) -> c * (...) shifts the log-likelihood by -ny log c."""
     from carma_pack_b200 import synth
