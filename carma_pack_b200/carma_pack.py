@@ -178,7 +178,8 @@ class CarmaModel(object):
         trace = res["samples"].reshape(-1, d)
         logpost = res["logposts"].reshape(-1)
         if p == 1:
-            sample = Car1Sample(self.time, self.y, self.ysig, trace=trace, logpost=logpost, series=self.series, prior=prior)
+            sample = Car1Sample(self.time, self.y, self.ysig, trace=trace, logpost=logpost, series=self.series,
+                                prior=prior)
         else:
             sample = CarmaSample(self.time, self.y, self.ysig, trace=trace, logpost=logpost, p=p, q=q,
                                  series=self.series, prior=prior)
@@ -338,13 +339,27 @@ class MCMCSample(object):
 class CarmaSample(MCMCSample):
     """MCMC samples of a CARMA(p,q) model with derived quantities (carma_pack.py:263-546)."""
 
-    def __init__(self, time, y, ysig, trace, logpost, p, q=0, series=None, prior=None, MLE=None):
+    def __init__(self, time, y, ysig, sampler=None, q=0, filename=None, MLE=None, trace=None, logpost=None, p=None,
+                 series=None, prior=None):
+        """Reference signature (carma_pack.py:267): CarmaSample(time, y, ysig, sampler, q=0, filename=None,
+        MLE=None) with `sampler` the object returned by run_mcmc_carma.  Alternatively pass trace/logpost
+        arrays.  As in the reference, p is taken from the trace width minus 3 minus q (so a caller that
+        forgets q gets p = p_true + q_true, which the reference's own test relies on: testCarmcmc.py:96)."""
+        if sampler is not None:
+            trace = np.array([list(r) for r in sampler.getSamples()], dtype=float)
+            logpost = np.array(list(sampler.GetLogLikes()), dtype=float)
+        if trace is None or logpost is None:
+            raise ValueError("CarmaSample needs either a sampler object or trace and logpost arrays")
+        trace = np.asarray(trace, dtype=float)
+        logpost = np.asarray(logpost, dtype=float)
+        if p is None:
+            p = trace.shape[1] - 3 - q
         super(CarmaSample, self).__init__(trace=trace, logpost=logpost)
+        time, y, ysig = np.asarray(time, float), np.asarray(y, float), np.asarray(ysig, float)
         self.time, self.y, self.ysig = time, y, ysig
         self.p, self.q = p, q
         self._series = series if series is not None else Series(time, y, ysig)
         self._prior = prior if prior is not None else self._series.default_prior(True)
-        trace = np.asarray(trace)
         # column names as samplers.py / carma_pack.py:286-305
         self._samples["var"] = trace[:, 0] ** 2
         self._samples["measerr_scale"] = trace[:, 1]
@@ -380,9 +395,18 @@ class CarmaSample(MCMCSample):
         self._samples["psd_width"] = -roots.real / (2.0 * np.pi)
         self._samples["psd_centroid"] = np.abs(roots.imag) / (2.0 * np.pi)
 
+    @staticmethod
+    def _poly_from_roots(roots):
+        """Row-wise np.poly (coefficients of prod (x - r_k), highest order first), vectorised over samples."""
+        n, k = roots.shape
+        coefs = np.zeros((n, k + 1), dtype=complex)
+        coefs[:, 0] = 1.0
+        for i in range(k):
+            coefs[:, 1:i + 2] = coefs[:, 1:i + 2] - roots[:, i:i + 1] * coefs[:, 0:i + 1]
+        return coefs
+
     def _ar_coefs(self):  # carma_pack.py:500-509
-        roots = self._samples["ar_roots"]
-        self._samples["ar_coefs"] = np.array([np.poly(r).real for r in roots])
+        self._samples["ar_coefs"] = self._poly_from_roots(self._samples["ar_roots"]).real
 
     def _ma_coefs(self, trace):  # carma_pack.py:469-498
         n = trace.shape[0]
@@ -399,11 +423,8 @@ class CarmaSample(MCMCSample):
             roots[:, 2 * i + 1] = -0.5 * (q2 - sq)
         if self.q % 2 == 1:
             roots[:, -1] = -qc[:, -1]
-        coefs = np.empty((n, self.q + 1))
-        for i in range(n):
-            c = np.poly(roots[i])
-            coefs[i] = (c / c[self.q])[::-1].real
-        self._samples["ma_coefs"] = coefs
+        c = self._poly_from_roots(roots)
+        self._samples["ma_coefs"] = (c / c[:, self.q:self.q + 1])[:, ::-1].real
 
     def _sigma_noise(self):  # carma_pack.py:511-546
         var, roots, ma = self._samples["var"], self._samples["ar_roots"], self._samples["ma_coefs"]
@@ -468,11 +489,19 @@ class CarmaSample(MCMCSample):
 class Car1Sample(MCMCSample):
     """MCMC samples of a CAR(1) model (carma_pack.py:866-1035, values only)."""
 
-    def __init__(self, time, y, ysig, trace, logpost, series=None, prior=None):
+    def __init__(self, time, y, ysig, sampler=None, filename=None, trace=None, logpost=None, series=None, prior=None):
+        """Reference signature (carma_pack.py:870): Car1Sample(time, y, ysig, sampler, filename=None)."""
+        if sampler is not None:
+            trace = np.array([list(r) for r in sampler.getSamples()], dtype=float)
+            logpost = np.array(list(sampler.GetLogLikes()), dtype=float)
+        if trace is None or logpost is None:
+            raise ValueError("Car1Sample needs either a sampler object or trace and logpost arrays")
+        trace = np.asarray(trace, dtype=float)
+        logpost = np.asarray(logpost, dtype=float)
         super(Car1Sample, self).__init__(trace=trace, logpost=logpost)
+        time, y, ysig = np.asarray(time, float), np.asarray(y, float), np.asarray(ysig, float)
         self.time, self.y, self.ysig = time, y, ysig
         self.p, self.q = 1, 0
-        trace = np.asarray(trace)
         self._series = series if series is not None else Series(time, y, ysig)
         self._prior = prior if prior is not None else self._series.default_prior(True)
         self._samples["var"] = trace[:, 0] ** 2

@@ -179,3 +179,35 @@ def test_choose_order_small_grid(cm):
     assert abs(-m1.fun - want) < 1e-8 * abs(want)
     k = 2 + 1
     assert abs(aicc[0] - (2 * k + 2 * model.get_mle(1, 0, ntrials=24, seed=7).fun + 2 * k * (k + 1) / (t.size - k - 1))) < 0.5
+
+
+def test_reference_package_name_and_flows(cm, small):
+    """`import carmcmc` keeps working, and the bodies of the reference's testCarp / testCarpq / testCar1
+    (src/tests/testCarmcmc.py:36-104) run unchanged against it."""
+    import carmcmc
+    s = small
+    xdata, ydata, dydata = carmcmc.vecD(), carmcmc.vecD(), carmcmc.vecD()
+    xdata.extend(s["x"]); ydata.extend(s["y"]); dydata.extend(s["dy"])
+    # testCar1
+    cppSample = carmcmc.run_mcmc_car1(100, 10, xdata, ydata, dydata, 1)
+    psampler = carmcmc.Car1Sample(s["x"], s["y"], s["dy"], cppSample)
+    assert psampler.p == 1
+    psamples = np.array(cppSample.getSamples())
+    ploglikes = np.array(cppSample.GetLogLikes())
+    sample0 = carmcmc.vecD(); sample0.extend(psamples[0])
+    assert np.isfinite(cppSample.getLogPrior(sample0))
+    assert round(abs(ploglikes[0] - cppSample.getLogDensity(sample0)), 7) == 0
+    # testCarp (pModel=3) and testCarpq (pModel=3, qModel=2): note the reference's own p = p+q quirk
+    for pModel, qModel in [(3, 0), (3, 2)]:
+        sampler = carmcmc.run_mcmc_carma(100, 10, xdata, ydata, dydata, pModel, qModel, 2, False, 1)
+        psampler = carmcmc.CarmaSample(np.array(xdata), np.array(ydata), np.array(dydata), sampler)
+        assert psampler.p == pModel + qModel
+        psamples = np.array(sampler.getSamples())
+        ploglikes = np.array(sampler.GetLogLikes())
+        sample0 = carmcmc.vecD(); sample0.extend(psamples[0])
+        assert round(abs(ploglikes[0] - sampler.getLogDensity(sample0)), 7) == 0
+    # README flow
+    model = carmcmc.CarmaModel(s["x"], s["y"], s["dy"], p=2, q=0)
+    smp = model.run_mcmc(50)
+    assert smp.get_samples("sigma").shape == (50, 1)
+    assert carmcmc.get_ar_roots(np.array([0.01]), np.array([0.2])).shape == (2,)
