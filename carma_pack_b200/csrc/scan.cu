@@ -46,8 +46,11 @@ struct FiltState {
 
 template <int P>
 __global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma_prior_t prior,
-                                   const double* __restrict__ theta, ScanParams<P>* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+                                   const double* __restrict__ theta, ScanParams<P>* __restrict__ out, int nrows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    theta += (size_t)row * d;
+    out += row;
     double th[MAX_D];
     for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[j] : 0.0;
     double Vr[P * (P + 1) / 2];
@@ -331,6 +334,9 @@ template <int P>
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_reduce_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
                    ScanElem<P>* __restrict__ E) {
+    // blockIdx.y = theta row: every per-row array is offset by it
+    spp += blockIdx.y;
+    E += (size_t)blockIdx.y * nchunks;
     const int m = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     if (m >= nchunks || spp->status != TT_OK) return;
     const ScanParams<P>& sp = *spp;
@@ -356,6 +362,10 @@ template <int P>
 __global__ void __launch_bounds__(256)
 scan_prefix_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ E, int M, int R, int T,
                    ScanElem<P>* __restrict__ X /* 2*T */, FiltState<P>* __restrict__ F /* M */) {
+    spp += blockIdx.x;  // one block per theta row
+    E += (size_t)blockIdx.x * M;
+    X += (size_t)blockIdx.x * 2 * T;
+    F += (size_t)blockIdx.x * M;
     if (spp->status != TT_OK) return;
     const int t = threadIdx.x;
     const int lo = t * R, hi = min(M, lo + R);
@@ -408,6 +418,9 @@ template <int P>
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
                    const FiltState<P>* __restrict__ F, double* __restrict__ LL) {
+    spp += blockIdx.y;
+    F += (size_t)blockIdx.y * nchunks;
+    LL += (size_t)blockIdx.y * nchunks;
     const int m = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     if (m >= nchunks || spp->status != TT_OK) return;
     const RealParams<P> prm = spp->prm;
@@ -438,6 +451,9 @@ template <int P>
 __global__ void __launch_bounds__(256)
 scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict__ LL, int M, double* __restrict__ out) {
     __shared__ double sh[256];
+    spp += blockIdx.x;  // one block per theta row
+    LL += (size_t)blockIdx.x * M;
+    out += blockIdx.x;
     if (spp->status != TT_OK) {
         if (threadIdx.x == 0) *out = -INFINITY;
         return;
@@ -453,9 +469,10 @@ scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict_
     if (threadIdx.x == 0) *out = sh[0] + spp->prm.logprior;
 }
 
+// nrows theta rows on one series: 5 launches in total (grid.y / one block per row)
 template <int P>
-static int scan_one(carma_series* s, int kind, int q, unsigned flags, const carma_prior_t& prior, const double* d_theta,
-                    double* d_out, int chunk, cudaStream_t st) {
+static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const carma_prior_t& prior, const double* d_theta,
+                     double* d_out, int nrows, int chunk, cudaStream_t st) {
     SeriesView sv = s->view();
     const int d = model_dim(kind, P, q);
     if (chunk <= 0) chunk = 128;
@@ -464,23 +481,25 @@ static int scan_one(carma_series* s, int kind, int q, unsigned flags, const carm
     int T = std::min(256, M);
     const int R = (M + T - 1) / T;
     T = (M + R - 1) / R;
-    size_t bytes = 256 + sizeof(ScanParams<P>) + (size_t)M * sizeof(ScanElem<P>) + 2 * (size_t)T * sizeof(ScanElem<P>) +
-                   (size_t)M * sizeof(FiltState<P>) + (size_t)M * sizeof(double) + 1024;
-    if (!s->scratch_misc.reserve(bytes)) return CARMA_ERR_CUDA;
-    char* base = (char*)s->scratch_misc.p;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_sp = align((size_t)nrows * sizeof(ScanParams<P>));
+    const size_t b_E = align((size_t)nrows * M * sizeof(ScanElem<P>));
+    const size_t b_X = align((size_t)nrows * 2 * T * sizeof(ScanElem<P>));
+    const size_t b_F = align((size_t)nrows * M * sizeof(FiltState<P>));
+    const size_t b_LL = align((size_t)nrows * M * sizeof(double));
+    if (!s->scratch_misc.reserve(b_sp + b_E + b_X + b_F + b_LL + 256)) return CARMA_ERR_CUDA;
+    char* base = (char*)s->scratch_misc.p;
     ScanParams<P>* sp = (ScanParams<P>*)base;
-    size_t off = align(sizeof(ScanParams<P>));
-    ScanElem<P>* E = (ScanElem<P>*)(base + off); off += align((size_t)M * sizeof(ScanElem<P>));
-    ScanElem<P>* X = (ScanElem<P>*)(base + off); off += align(2 * (size_t)T * sizeof(ScanElem<P>));
-    FiltState<P>* F = (FiltState<P>*)(base + off); off += align((size_t)M * sizeof(FiltState<P>));
-    double* LL = (double*)(base + off);
-    scan_params_kernel<P><<<1, 32, 0, st>>>(kind, q, d, flags, prior, d_theta, sp);
-    unsigned grid = (unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    ScanElem<P>* E = (ScanElem<P>*)(base + b_sp);
+    ScanElem<P>* X = (ScanElem<P>*)(base + b_sp + b_E);
+    FiltState<P>* F = (FiltState<P>*)(base + b_sp + b_E + b_X);
+    double* LL = (double*)(base + b_sp + b_E + b_X + b_F);
+    scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, d_theta, sp, nrows);
+    dim3 grid((unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK), (unsigned)nrows);
     scan_reduce_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, E);
-    scan_prefix_kernel<P><<<1, 256, 0, st>>>(sp, E, M, R, T, X, F);
+    scan_prefix_kernel<P><<<nrows, 256, 0, st>>>(sp, E, M, R, T, X, F);
     scan_filter_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL);
-    scan_sum_kernel<P><<<1, 256, 0, st>>>(sp, LL, M, d_out);
+    scan_sum_kernel<P><<<nrows, 256, 0, st>>>(sp, LL, M, d_out);
     return cuda_ok(cudaGetLastError(), "scan kernels launch") ? CARMA_OK : CARMA_ERR_CUDA;
 }
 
@@ -501,18 +520,23 @@ int carma_loglik_scan_dev(carma_series_t s, int kind, int p, int q, const carma_
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
     const size_t d = (size_t)model_dim(kind, p, q);
     cudaStream_t st = (cudaStream_t)stream;
-    for (size_t i = 0; i < n; i++) {
+    // rows are processed in groups so that the per-row scratch stays below ~1 GiB (and grid.y <= 65535)
+    const size_t chunk_eff = chunk > 0 ? (size_t)std::max(chunk, 2) : 128;
+    size_t per_row = ((size_t)s->ny / chunk_eff + 2) * (size_t)(4 * p * p + 3 * p + 1) * sizeof(double) * 2;
+    size_t group = std::max<size_t>(1, std::min<size_t>(n, std::min<size_t>(4096, ((size_t)1 << 30) / std::max<size_t>(per_row, 1))));
+    for (size_t i0 = 0; i0 < n; i0 += group) {
+        const int nr = (int)std::min(group, n - i0);
+        const double* th = d_theta + i0 * d;
+        double* out = d_logpost + i0;
         int rc;
-        const double* th = d_theta + i * d;
-        double* out = d_logpost + i;
         switch (p) {
-            case 1: rc = scan_one<1>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 2: rc = scan_one<2>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 3: rc = scan_one<3>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 4: rc = scan_one<4>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 5: rc = scan_one<5>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 6: rc = scan_one<6>(s, kind, q, flags, *prior, th, out, chunk, st); break;
-            case 7: rc = scan_one<7>(s, kind, q, flags, *prior, th, out, chunk, st); break;
+            case 1: rc = scan_rows<1>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 2: rc = scan_rows<2>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 3: rc = scan_rows<3>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 4: rc = scan_rows<4>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 5: rc = scan_rows<5>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 6: rc = scan_rows<6>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
+            case 7: rc = scan_rows<7>(s, kind, q, flags, *prior, th, out, nr, chunk, st); break;
             default: rc = CARMA_ERR_ARG;
         }
         if (rc) return rc;

@@ -211,3 +211,24 @@ def test_reference_package_name_and_flows(cm, small):
     smp = model.run_mcmc(50)
     assert smp.get_samples("sigma").shape == (50, 1)
     assert carmcmc.get_ar_roots(np.array([0.01]), np.array([0.2])).shape == (2,)
+
+
+def test_simulate_is_conditional_draw(cm, kelly):
+    """KalmanFilter::Simulate (kfilter.hpp:135-184): draws at one new time follow N(Predict mean, Predict var);
+    two simulated times are positively correlated when close (the first draw is inserted before the second)."""
+    m = cm._carmcmc_mod
+    n = 80
+    t, y, e = kelly["t"][:n], kelly["y"][:n], kelly["yerr"][:n]
+    kf = m.KalmanFilterp(m.vecD(t), m.vecD(y), m.vecD(e), float(kelly["sigsqr"]),
+                         m.vecC([complex(z) for z in kelly["roots"]]), m.vecD(kelly["ma"]))
+    tq = 0.5 * (t[30] + t[31])
+    pred = kf.Predict(tq)
+    m.set_seed(99)
+    draws = np.array([kf.Simulate(m.vecD([tq]))[0] for _ in range(300)])
+    assert abs(draws.mean() - pred.first) < 4 * np.sqrt(pred.second / 300)
+    assert 0.7 < draws.var() / pred.second < 1.4
+    pairs = np.array([list(kf.Simulate(m.vecD([tq, tq + 0.2]))) for _ in range(200)])
+    assert np.corrcoef(pairs[:, 0], pairs[:, 1])[0, 1] > 0.5
+    # the filter object is restored afterwards
+    kf.Filter()
+    np.testing.assert_allclose(np.array(kf.GetVar()), kelly["var"][:n], rtol=1e-9)
