@@ -17,6 +17,9 @@
  *   - `*_dev` entry points take DEVICE pointers and a cudaStream_t (passed as void*), do no
  *     synchronisation and no host<->device copies; the plain variants take HOST pointers,
  *     copy in/out and synchronise before returning.
+ *   - a series object owns device scratch buffers: calls on ONE object must not run concurrently
+ *     (host calls from several threads, or `*_dev` calls on different streams without ordering);
+ *     different objects are independent.  carma_last_error() is thread-local.
  *   - theta rows are laid out as the reference's value_ vectors (src/include/carpack.hpp:131-176):
  *       CAR1  : [sigma_y, measerr_scale, mu, log(omega)]                        d = 4
  *       CARp  : [sigma_y, measerr_scale, mu, log-quad AR terms (p)]             d = 3+p

@@ -85,3 +85,22 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
                 assert "carma_oracle" not in txt, f
+
+
+def test_reference_package_alias_imports_on_cpu():
+    """`import carmcmc` (the reference's package name) resolves to this implementation without a GPU."""
+    import carmcmc
+    for name in ("vecD", "vecvecD", "vecC", "pairD", "CAR1", "CARp", "CARMA", "run_mcmc_car1", "run_mcmc_carma",
+                 "KalmanFilter1", "KalmanFilterp", "CarmaModel", "CarmaSample", "Car1Sample", "power_spectrum",
+                 "carma_variance", "carma_process", "get_ar_roots", "MCMCSample"):
+        assert hasattr(carmcmc, name), name
+    v = carmcmc.vecD()
+    v.extend([1.0, 2.0])
+    v.append(3.0)
+    assert len(v) == 3 and list(v) == [1.0, 2.0, 3.0] and v[1] == 2.0
+    c = carmcmc.vecC()
+    c.append(1 + 2j)
+    assert c[0] == 1 + 2j
+    pr = carmcmc.pairD()
+    pr.first, pr.second = 1.5, 2.5
+    assert (pr.first, pr.second) == (1.5, 2.5)
