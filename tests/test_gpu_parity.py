@@ -252,6 +252,43 @@ def test_loglik_long_series_chunked_pipeline(C, O, kelly):
     s1.close(); s2.close()
 
 
+def test_loglik_stress_all_orders(C, O):
+    """Every (p,q) of the choose_order grid (p = 1..7, q < p), random parameter vectors including overdamped
+    (real-pair) roots and out-of-prior rows, with and without bounds, on an irregular series."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(2024)
+    t = synth.cauchy_times(140, rng)
+    y = 1.0 + np.cumsum(rng.standard_normal(140)) * 0.1 + 0.05 * rng.standard_normal(140)
+    e = 0.05 * rng.uniform(0.5, 2.0, 140)
+    s = C.Series(t, y, e)
+    pr = s.default_prior()
+    opr = O.default_prior(t, y)
+    total_ill = 0
+    for p in range(1, 8):
+        for q in range(p):
+            if p == 1:
+                kind, okind = C.KIND_CAR1, O.KIND_CAR1
+                th = np.column_stack([y.std() * np.exp(0.3 * rng.standard_normal(150)), rng.uniform(0.4, 2.1, 150),
+                                      y.mean() + 0.2 * rng.standard_normal(150), rng.uniform(-8, 3, 150)])
+            else:
+                kind, okind = (C.KIND_CARMA, O.KIND_CARMA) if q > 0 else (C.KIND_CARP, O.KIND_CARP)
+                th = synth.prior_draws(150, p, q, t, y, rng)
+                # push a third of the rows into the overdamped regime (two real roots in the first factor)
+                th[::3, 3] = th[::3, 4] * 2 - np.log(4.0) - rng.uniform(0.1, 2.0, th[::3].shape[0])
+            for flags, ign in ((0, False), (C.IGNORE_BOUNDS, True)):
+                if p == 1 and ign:
+                    continue
+                got = s.loglik(kind, p, q, th, prior=pr, flags=flags)
+                want = O.logdensity(okind, p, q, t, y, e, th, prior=opr, ignore_prior=ign)
+                want_ld = O.logdensity(okind, p, q, t, y, e, th, prior=opr, ignore_prior=ign, long_double=True)
+                total_ill += assert_logpost_parity(
+                    got, want, want_ld, max_illcond_frac=0.15, what="stress p=%d q=%d ign=%d" % (p, q, ign),
+                    ulp_eval=lambda rows, k: O.logdensity(okind, p, q, t, y, e, ulp_shift(th[rows], k), prior=opr,
+                                                          ignore_prior=ign))
+    print("stress: %d rows needed the noise-floor criterion" % total_ill)
+    s.close()
+
+
 def test_async_pipeline_equals_blocking_call(C):
     """carma_loglik_batch_async/_wait (two slots) returns exactly what the blocking call returns."""
     from carma_pack_b200 import synth
