@@ -166,6 +166,9 @@ struct KalmanReal {
 
 // Running sum of -1/2 log(var_i) - 1/2 innov_i^2 / var_i with the logs folded into one log of a
 // product of mantissas (exponents summed as integers): log() leaves the time loop.
+// out-of-line: keeps the (never taken in practice) log() code out of the time loop's instruction footprint
+static __device__ __noinline__ double loglik_slow_log(double var) { return log(var); }
+
 struct LogLikAcc {
     double quad;    // sum innov^2 / var
     double prod;    // product of mantissas of var, renormalised
@@ -186,7 +189,7 @@ struct LogLikAcc {
                 n_in_prod = 0;
             }
         } else {
-            logsum += log(var);  // NaN for var < 0 or NaN, -inf for 0: same class as the reference
+            logsum += loglik_slow_log(var);  // NaN for var < 0 or NaN, -inf for 0: same class as the reference
         }
     }
     __device__ __forceinline__ double value() const {
