@@ -481,6 +481,59 @@ class CarmaSample(MCMCSample):
         mean, var = self._series.filter(sigsqr, roots, ma, measerr_scale=scale, mu=mu)
         return mean + mu, var
 
+    def simulate(self, time, bestfit="map", seed=None):
+        """Conditional simulation of the light curve at `time` given the data (carma_pack.py:830-854 ->
+        KalmanFilterp::Simulate): sequential draw-and-insert, each draw through the GPU Predict."""
+        from . import _carmcmc as m
+        idx = self.best_index() if bestfit == "map" else int(bestfit)
+        sigsqr, roots, ma, mu, scale = self._params_at(idx)
+        if seed is not None:
+            m.set_seed(int(seed))
+        kf = m.KalmanFilterp(m.vecD(self.time), m.vecD(self.y - mu), m.vecD(np.sqrt(scale) * self.ysig), sigsqr,
+                             m.vecC([complex(r) for r in roots]), m.vecD(ma))
+        order = np.argsort(np.atleast_1d(time))
+        ysim = np.array(kf.Simulate(m.vecD(np.atleast_1d(time)[order])))
+        out = np.empty_like(ysim)
+        out[order] = ysim
+        return out + mu
+
+    def psd_credible_band(self, percentile=68.0, nsamples=None, freq=None, seed=0):
+        """Numeric part of plot_power_spectrum (carma_pack.py:548-612): pointwise credibility band of the
+        power spectrum over the posterior.  Returns (psd_lo, psd_hi, psd_mid, freq)."""
+        sigmas = np.ravel(self._samples["sigma"])
+        ar_coefs = self._samples["ar_coefs"]
+        ma_coefs = self._samples["ma_coefs"]
+        n = sigmas.size
+        if nsamples is None or nsamples > n:
+            nsamples = n
+        pick = np.random.default_rng(seed).permutation(n)[:nsamples]
+        if freq is None:
+            dt = np.diff(self.time)
+            freq = np.logspace(np.log10(1.0 / (self.time.max() - self.time.min())), np.log10(0.5 / dt.min()), 200)
+        s = 2.0j * np.pi * freq
+        num = np.zeros((nsamples, freq.size), dtype=complex)
+        den = np.zeros((nsamples, freq.size), dtype=complex)
+        for k in range(ma_coefs.shape[1]):
+            num += ma_coefs[pick, k:k + 1] * s[None, :] ** k
+        for k in range(ar_coefs.shape[1]):
+            den += ar_coefs[pick, k:k + 1] * s[None, :] ** (ar_coefs.shape[1] - 1 - k)
+        psd = sigmas[pick, None] ** 2 * np.abs(num) ** 2 / np.abs(den) ** 2
+        lo, hi = (100.0 - percentile) / 2.0, 100.0 - (100.0 - percentile) / 2.0
+        return np.percentile(psd, lo, axis=0), np.percentile(psd, hi, axis=0), np.median(psd, axis=0), freq
+
+    def assess_fit_values(self, bestfit="map", nlags=20):
+        """Numeric part of assess_fit (carma_pack.py:687-744): standardized one-step residuals and the
+        autocorrelation of the residuals and of their squares (white under a good fit)."""
+        mean, var = self.kalman_filter(bestfit)
+        resid = (self.y - mean) / np.sqrt(var)
+
+        def acf(x):
+            x = x - x.mean()
+            full = np.correlate(x, x, mode="full")[x.size - 1:]
+            return full[:nlags + 1] / full[0]
+
+        return resid, acf(resid), acf(resid ** 2), 1.96 / np.sqrt(resid.size)
+
     def DIC(self):  # carma_pack.py:808-828
         loglik = np.ravel(self._samples["loglik"])
         return -2.0 * loglik.mean() + 2.0 * np.var(-2.0 * loglik) / 2.0

@@ -150,6 +150,17 @@ def test_carma_model_run_mcmc_and_sample(cm):
     chi = (y - mean) / np.sqrt(var)
     assert 0.5 < chi.std() < 2.0  # standardized residuals are O(1) (assess_fit, carma_pack.py:687-744)
     assert np.isfinite(sample.DIC())
+    resid, acf1, acf2, bound = sample.assess_fit_values()
+    assert resid.shape == y.shape and abs(acf1[0] - 1.0) < 1e-12 and np.mean(np.abs(acf1[1:]) < 3 * bound) > 0.8
+    lo, hi, mid, freq = sample.psd_credible_band(percentile=95.0, nsamples=200)
+    assert np.all(lo <= mid) and np.all(mid <= hi) and freq.shape == mid.shape
+    # power_spectrum() of the MAP sample sits inside its own posterior band at most frequencies
+    i0 = sample.best_index()
+    psd_map = cm.power_spectrum(freq, float(sample._samples["sigma"][i0][0]), sample._samples["ar_coefs"][i0],
+                                sample._samples["ma_coefs"][i0])
+    assert np.mean((psd_map >= lo) & (psd_map <= hi)) > 0.7
+    ysim = sample.simulate(np.array([t[-1] + 1.0, t[10] + 0.01, t[-1] + 5.0]), seed=4)
+    assert ysim.shape == (3,) and np.all(np.isfinite(ysim))
     # CAR(1) path
     m1 = cm.CarmaModel(t, y, e, p=1)
     s1 = m1.run_mcmc(200, seed=4)
