@@ -53,11 +53,13 @@ __device__ __forceinline__ double exp_fast(double x) {
     double tj = __ldg(&kExp2Tab[k & 31]);
     double p = fma(tj, pm1, tj);              // 2^(j/32) e^r
     int n = k >> 5;
-    // 2^n by exponent construction; results below the normal range are flushed to zero
-    int nn = max(n, -1022);
+    // 2^n by exponent construction; results below the normal range are flushed to zero.  The decision is
+    // taken on x itself, so arguments far below the range of the magic-number rounding (|x| > 2^51 ln2/32)
+    // still give exactly 0 instead of garbage.
+    int nn = min(max(n, -1022), 1023);
     double s = __hiloint2double((nn + 1023) << 20, 0);
     double res = p * s;
-    return (n < -1022) ? 0.0 : res;
+    return (x < -708.0) ? 0.0 : res;
 }
 
 __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
