@@ -77,6 +77,7 @@ struct PTMulti {
     int max_nyp;
     int enabled;
     unsigned long long ens_per_curve;
+    int resident;  // 1: the series is staged in shared memory; 0: too long, read from global memory (L1/L2)
 };
 
 // ---- starting-value RNG (mirrors oracle StartRng draw for draw) ---------------------------------
@@ -143,7 +144,7 @@ __device__ __noinline__ double logdensity_resident(const PTParams& pp, const dou
     LogLikAcc acc;
     kf.reset(prm, e2_0);
     acc.init();
-    filter_span<P>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+    filter_span_any<P, true>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
     return acc.value() + prm.logprior;
 }
 
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
     const size_t gtid = (size_t)blockIdx.x * PT_BLOCK + tid;
     unsigned long long ens;
     bool active;
-    const int nyp = mm.enabled ? mm.max_nyp : sv.nyp;
+    const int nyp = mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0;
 
     double* sdt = smem;
     double* sy = smem + nyp;
@@ -217,24 +218,37 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         pp.prior = ci.prior;
         pp.y_mean = ci.y_mean; pp.y_var_sample = ci.y_var_sample; pp.y_var_pop = ci.y_var_pop;
         pp.median_dt = ci.median_dt; pp.tspan = ci.tspan; pp.ny = ny;
-        for (int k = tid; k < ny; k += PT_BLOCK) {
-            sdt[k] = mm.dt[o0 + k];
-            sy[k] = mm.y[o0 + k];
-            se[k] = mm.e2[o0 + k];
+        if (mm.resident) {
+            for (int k = tid; k < ny; k += PT_BLOCK) {
+                sdt[k] = mm.dt[o0 + k];
+                sy[k] = mm.y[o0 + k];
+                se[k] = mm.e2[o0 + k];
+            }
+            __syncthreads();
+        } else {
+            sdt = const_cast<double*>(mm.dt + o0);
+            sy = const_cast<double*>(mm.y + o0);
+            se = const_cast<double*>(mm.e2 + o0);
         }
-        __syncthreads();
         e2_0 = se[0];
         se = se + 1;
     } else {
         ens = (unsigned long long)blockIdx.x * epb + e_local;
         active = (e_local < epb) && (ens < pp.n_ens);
-        // ---- stage the light curve once (TMA bulk copy), resident for the whole run
+        // ---- stage the light curve once (TMA bulk copy), resident for the whole run; a series that does
+        // not fit in shared memory is read from global memory instead (every lane reads the same address:
+        // one L1 line per warp, and the filter loop prefetches one step ahead)
+        if (!mm.resident) {
+            sdt = const_cast<double*>(sv.dt);
+            sy = const_cast<double*>(sv.y);
+            se = const_cast<double*>(sv.e2n);
+        }
         if (tid == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && mm.resident) {
             // pieces of at most 64 KiB keep every transaction count far below the mbarrier tx limit
             const uint32_t total = (uint32_t)(3 * (size_t)sv.nyp * 8);
             mbar_expect_tx(&bar, total);
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
                 bulk_g2s((char*)smem + o, (const char*)sv.dt + o, b, &bar);
             }
         }
-        mbar_wait(&bar, 0);
+        if (mm.resident) mbar_wait(&bar, 0);
         e2_0 = sv.e2_0;
     }
 
@@ -440,7 +454,7 @@ static size_t pt_smem_bytes(int nyp, int d) {
 template <int P>
 static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t chol_stride, unsigned grid,
                              cudaStream_t stream, const PTMulti& mm) {
-    size_t smem = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d);
+    size_t smem = pt_smem_bytes(mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0, pp.d);
     cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
@@ -532,10 +546,8 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         grid = (unsigned)(m->ncurves * (size_t)mm.blocks_per_curve);
         scratch = &m->scratch_misc;
     }
-    if (pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) > 220 * 1024) {
-        set_error("carma_pt_run: series too long for the resident-series MCMC kernel (ny <= ~9000)");
-        return CARMA_ERR_ARG;
-    }
+    // series resident in shared memory when it fits (<= 96 KiB keeps at least two blocks per SM)
+    mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= 96 * 1024 ? 1 : 0;
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
     if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;

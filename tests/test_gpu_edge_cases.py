@@ -125,13 +125,25 @@ def test_error_paths(C):
     with pytest.raises(C.CarmaError):
         s.pt_run(C.KIND_CARP, 2, 0, 5, 5, dof=7)                  # odd Student-t dof is not supported
     s.close()
-    tl = np.arange(12000.0)
-    sl = C.Series(tl, np.sin(tl), np.ones(tl.size))
-    with pytest.raises(C.CarmaError):                             # resident-series MCMC kernel: ny too large
-        sl.pt_run(C.KIND_CARP, 2, 0, 5, 5, ntemps=2)
-    assert np.isfinite(sl.loglik(C.KIND_CARP, 2, 0, np.array([[1.0, 1.0, 0.0, -2.0, -1.0]]), flags=C.IGNORE_BOUNDS)[0])
-    sl.close()
     # the series object is still usable after errors
     s2 = C.Series(t, y, e)
     assert np.isfinite(s2.loglik(C.KIND_CARMA, 5, 3, synth.readme_theta(3))[0])
     s2.close()
+
+
+def test_pt_on_series_too_long_for_shared_memory(C, O):
+    """ny = 12,000 does not fit the resident-series staging: the sampler reads the series from global memory
+    and must give exactly the chain the oracle's sequential sampler produces from the same streams."""
+    rng = np.random.default_rng(12)
+    tl = np.cumsum(rng.uniform(0.5, 1.5, 12000))
+    yl = np.sin(tl / 30.0) + 0.3 * rng.standard_normal(tl.size)
+    el = np.full(tl.size, 0.3)
+    sl = C.Series(tl, yl, el)
+    pr = sl.default_prior()
+    res = sl.pt_run(C.KIND_CARP, 2, 0, 6, 6, ntemps=3, n_ensembles=2, seed=5, prior=pr)
+    assert np.all(np.isfinite(res["logposts"]))
+    relp = sl.loglik(C.KIND_CARP, 2, 0, res["samples"].reshape(-1, 5), prior=pr).reshape(res["logposts"].shape)
+    np.testing.assert_allclose(relp, res["logposts"], rtol=1e-9)
+    ores = O.pt_run(O.KIND_CARP, 2, 0, tl, yl, el, 6, 6, ntemps=3, seed=5, prior=O.default_prior(tl, yl))
+    np.testing.assert_allclose(res["samples"][0], ores["samples"], rtol=1e-7, atol=1e-9)
+    sl.close()
