@@ -205,18 +205,19 @@ class CarmaModel(object):
             hi += [np.inf] * q
         return np.array(lo), np.array(hi)
 
-    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0):
+    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0, series=None):
         """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
         in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
         global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
-        rank runs it)."""
+        rank runs it).  series: device series to use (choose_order gives each worker thread its own)."""
+        series = self.series if series is None else series
         kind = _kind_for(p, q)
         d = model_dim(kind, p, q)
         if seed is None:
             seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
-        prior = self.series.default_prior(population_var=True)
+        prior = series.default_prior(population_var=True)
         # initial guesses: nsamples=1, nburnin=25, nwalkers=10 MCMC runs (carma_pack.py:197-216)
-        res = self.series.pt_run(kind, p, q, 1, 25, ntemps=1 if p == 1 else 10, n_ensembles=ntrials, seed=seed,
+        res = series.pt_run(kind, p, q, 1, 25, ntemps=1 if p == 1 else 10, n_ensembles=ntrials, seed=seed,
                                  ensemble_offset=trial_offset, prior=prior)
         x0 = res["samples"][:, 0, :].copy()
         x0[:, 1] = 1.0  # carma_pack.py:216
@@ -228,8 +229,13 @@ class CarmaModel(object):
                     x0[i, j] = rng.uniform(lo[j], hi[j])
         flags = 0 if p == 1 else IGNORE_BOUNDS  # SetMLE(True) only for p > 1 (carma_pack.py:242)
 
-        def negloglik(th):
-            return -self.series.loglik(kind, p, q, th, prior=prior, flags=flags)  # _carma_loglik, carma_pack.py:255-260
+        def negloglik(th):  # _carma_loglik, carma_pack.py:255-260
+            # through the slot API: its own stream, so concurrent fits of other models overlap on the GPU
+            th = np.ascontiguousarray(th, dtype=np.float64)
+            out = np.empty(th.shape[0])
+            series.loglik_async(kind, p, q, th.ctypes.data, out.ctypes.data, th.shape[0], prior, 0, flags=flags)
+            series.loglik_wait(0)
+            return -out
 
         x, f, nit, nfev = batched_lbfgs(negloglik, x0, lo, hi, maxiter=maxiter)
         best = int(np.argmin(f))
@@ -265,11 +271,32 @@ class CarmaModel(object):
             for k in sorted(set(int(u) // ntrials for u in mine)):
                 tr = [int(u) % ntrials for u in mine if int(u) // ntrials == k]
                 units.append((k, min(tr), len(tr)))
-        local = {}
-        for k, first, count in units:
+        # The fits of different (p,q) models are independent and each one is a chain of small, latency-bound
+        # launches: run several of them concurrently from worker threads, each with its own device series
+        # (own scratch buffers and stream), so their launches overlap on the GPU.  Heaviest models first.
+        from concurrent.futures import ThreadPoolExecutor
+        units.sort(key=lambda u: -(pqlist[u[0]][0] ** 2) * (4 + sum(pqlist[u[0]])) * u[2])
+        nworkers = max(1, min(8, len(units)))
+        pool_series = [Series(self.time, self.y, self.ysig, device=self.device) for _ in range(nworkers)]
+        import queue
+        free = queue.Queue()
+        for srs in pool_series:
+            free.put(srs)
+
+        def fit(unit):
+            k, first, count = unit
             p, q = pqlist[k]
-            local[k] = self.get_mle(p, q, ntrials=count, njobs=njobs, seed=None if seed is None else seed + k,
-                                    trial_offset=first)
+            srs = free.get()
+            try:
+                return k, self.get_mle(p, q, ntrials=count, njobs=njobs, seed=None if seed is None else seed + k,
+                                       trial_offset=first, series=srs)
+            finally:
+                free.put(srs)
+
+        with ThreadPoolExecutor(max_workers=nworkers) as ex:
+            local = dict(ex.map(fit, units))
+        for srs in pool_series:
+            srs.close()
         if world > 1:
             from . import sharding
             dmax = max(3 + p + q for p, q in pqlist)
