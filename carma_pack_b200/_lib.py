@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcarma_b200.so")
+LIB_PATH = os.environ.get("CARMA_B200_LIB") or os.path.join(_HERE, "libcarma_b200.so")  # override: tuning builds
 
 KIND_CAR1, KIND_CARP, KIND_CARMA, KIND_ZCAR, KIND_ZCARMA = 0, 1, 2, 3, 4
 IGNORE_BOUNDS, LOGLIK_ONLY = 1, 2
