@@ -79,13 +79,23 @@ struct KalmanReal {
         for (int s = 0; s < NS; s++) {
             // the decay factor of the first root is common to both slot types
             double e = exp_fast(prm.lam[2 * s] * dt);
-            if (ALLC || ((prm.cmask >> s) & 1u)) {
-                double sn, cs;
-                sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
+            double sn, cs;
+            sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
+            if (ALLC) {
                 f00[s] = e * cs; f01[s] = -(e * sn); f10[s] = e * sn; f11[s] = e * cs;
             } else {
-                f00[s] = e; f01[s] = 0.0; f10[s] = 0.0;
-                f11[s] = exp_fast(prm.lam[2 * s + 1] * dt);
+                // generic loop: BOTH candidates are evaluated for every lane (lam[2s+1] <= 0 in either
+                // reading, so the extra exp is harmless) and selected per lane -- straight-line code.  A
+                // per-lane branch here costs more than the 12 extra FP64 instructions: mixed warps would
+                // run both sides anyway and the split basic blocks stop ptxas from interleaving the chains
+                // (measured: PT-MCMC config 3, 159 -> 140 ms).
+                const bool is_c = (prm.cmask >> s) & 1u;
+                const double e2 = exp_fast(prm.lam[2 * s + 1] * dt);
+                const double ec = e * cs, es = e * sn;
+                f00[s] = is_c ? ec : e;
+                f01[s] = is_c ? -es : 0.0;
+                f10[s] = is_c ? es : 0.0;
+                f11[s] = is_c ? ec : e2;
             }
         }
         double fo = 1.0;
