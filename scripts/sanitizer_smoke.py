@@ -1,0 +1,27 @@
+"""Small end-to-end run of every kernel family, sized for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import carma_pack_b200 as C
+from carma_pack_b200 import synth
+
+rng = np.random.default_rng(0)
+t, y, e = synth.readme_series(601, 3)          # > 512 points: double-buffered TMA path in K1
+s = C.Series(t, y, e)
+pr = s.default_prior()
+th = synth.theta_batch(200, t, y, seed=1)
+lp = s.loglik(C.KIND_CARMA, 5, 3, th, prior=pr)
+lp2 = s.loglik_scan(C.KIND_CARMA, 5, 3, th[:3], prior=pr, chunk=16)
+m, v = s.filter(1.0, [-0.1 + 0.3j, -0.1 - 0.3j, -0.05], [1.0, 0.5, 0.0])
+qm, qv = s.predict(1.0, [-0.1 + 0.3j, -0.1 - 0.3j, -0.05], [1.0, 0.5, 0.0], [t[0] - 1, t[5] + 0.1, t[-1] + 3])
+r = s.pt_run(C.KIND_CARMA, 5, 3, 4, 4, ntemps=10, n_ensembles=7, seed=2, prior=pr, record_trace=True)
+r1 = s.pt_run(C.KIND_CAR1, 1, 0, 4, 4, ntemps=1, n_ensembles=3, seed=2)
+ts, ys, es, off = [], [], [], [0]
+for c in range(9):
+    n = int(rng.integers(5, 60))
+    tt = np.cumsum(rng.uniform(0.5, 2, n)); ts.append(tt); ys.append(rng.standard_normal(n)); es.append(np.full(n, 0.2)); off.append(off[-1] + n)
+ms = C.MultiSeries(np.concatenate(ts), np.concatenate(ys), np.concatenate(es), off)
+thm = np.vstack([synth.prior_draws(1, 3, 1, ts[c], ys[c], rng) for c in range(9)])
+lm = ms.loglik(C.KIND_CARMA, 3, 1, thm)
+rm = ms.pt_run(C.KIND_CARMA, 3, 1, 3, 3, ntemps=4, n_ensembles=2, seed=4)
+print("ok", np.isfinite(lp).mean(), lp2[:2], m[:2], qv, r["logposts"].shape, r1["logposts"].shape, lm[:3], rm["logposts"].shape)
