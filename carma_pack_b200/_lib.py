@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "carma_loglik_batch_dev", "carma_loglik_batch", "carma_loglik_batch_async", "carma_loglik_batch_wait",
     "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
+    "carma_multi_series_simulate", "carma_multi_series_get_curve",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
@@ -88,6 +89,10 @@ def _load():
                                             ctypes.POINTER(_vp)]
     L.carma_multi_series_destroy.argtypes = [_vp]
     L.carma_multi_series_default_priors.argtypes = [_vp, ctypes.c_int, _vp]
+    L.carma_multi_series_simulate.argtypes = [_sz, _sz, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, pr,
+                                              ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                              ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.carma_multi_series_get_curve.argtypes = [_vp, _sz, _dp, _dp, _dp, _sz, ctypes.POINTER(_sz)]
     L.carma_multi_loglik_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
                                          ctypes.c_uint, _vp]
     L.carma_multi_loglik.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_uint]
@@ -295,6 +300,34 @@ class MultiSeries:
                                             ctypes.byref(self.handle)), "carma_multi_series_create")
         self.offsets = off
         self.device = device
+
+    @classmethod
+    def simulate(cls, ncurves, ny, kind, p, q, theta_true, yerr=0.05, dt_min=0.05, dt_max=50.0, seed=0,
+                 curve_offset=0, prior=None, device=0):
+        """ncurves synthetic light curves of ny points generated in HBM from the model theta_true
+        (carma_multi_series_simulate); nothing crosses PCIe except the per-curve statistics."""
+        th = _c(theta_true)
+        if th.shape != (model_dim(kind, p, q),):
+            raise ValueError("theta_true must have %d entries" % model_dim(kind, p, q))
+        self = cls.__new__(cls)
+        self.ncurves = int(ncurves)
+        self.handle = _vp()
+        pp = ctypes.byref(prior) if prior is not None else None
+        check(lib.carma_multi_series_simulate(int(ncurves), int(ny), kind, p, q, _ptr(th), pp, float(yerr),
+                                              float(dt_min), float(dt_max), int(seed), int(curve_offset), device,
+                                              ctypes.byref(self.handle)), "carma_multi_series_simulate")
+        self.offsets = np.arange(self.ncurves + 1, dtype=np.int64) * int(ny)
+        self.device = device
+        return self
+
+    def curve(self, c):
+        """(time, y, yerr) of curve c copied back to the host; time starts at 0."""
+        n = int(self.offsets[c + 1] - self.offsets[c])
+        t, y, e = np.empty(n), np.empty(n), np.empty(n)
+        got = _sz(0)
+        check(lib.carma_multi_series_get_curve(self.handle, int(c), _ptr(t), _ptr(y), _ptr(e), n, ctypes.byref(got)),
+              "carma_multi_series_get_curve")
+        return t, y, e
 
     def close(self):
         if getattr(self, "handle", None):

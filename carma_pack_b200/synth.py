@@ -144,6 +144,12 @@ def carma31_truth():
     return ar_roots, ma, sigsqr
 
 
+def carma31_theta(sigmay=1.0, mu=0.0):
+    """theta (sigma_y, measerr scale, mu, log-quadratic AR terms, log-quadratic MA terms) of carma31_truth()."""
+    ar_roots, ma, _ = carma31_truth()
+    return np.array([sigmay, 1.0, mu] + list(roots_to_logquad(ar_roots)) + [np.log(1.0 / ma[1])])
+
+
 def roots_to_logquad(ar_roots):
     """Inverse of CARp::ARRoots (carpack.cpp:137-172) for roots ordered as conjugate/real pairs
     followed by an optional single real root."""

@@ -125,6 +125,19 @@ int carma_multi_series_create(const double* time, const double* y, const double*
                               size_t ncurves, int device, carma_multi_series_t* out);
 int carma_multi_series_destroy(carma_multi_series_t m);
 int carma_multi_series_default_priors(carma_multi_series_t m, int population_var, carma_prior_t* out /* ncurves */);
+/* Synthetic survey generated in HBM (BASELINE config 5 at full size without a host round trip): ncurves
+ * light curves of ny points drawn from the model theta_true, the recipe of the reference's Python generator
+ * (carma_process, src/carmcmc/carma_pack.py:1148-1259: innovations form of the noise-free filter; sampling
+ * gaps dt_min + |Cauchy| truncated at dt_max as in cpp_tests/generate_test_data.py:17) plus N(0, yerr^2)
+ * measurement noise.  Curve c uses Philox chain curve_offset + c, so a survey does not depend on how it is
+ * sharded across GPUs.  prior: bounds used by the theta transform (NULL = wide open; kappa in (0, 1/dt_min)).
+ * The handle is an ordinary carma_multi_series_t (default priors and starting-value statistics included). */
+int carma_multi_series_simulate(size_t ncurves, size_t ny, int kind, int p, int q, const double* theta_true,
+                                const carma_prior_t* prior, double yerr, double dt_min, double dt_max, uint64_t seed,
+                                uint32_t curve_offset, int device, carma_multi_series_t* out);
+/* Copy curve `curve` back to the host (time measured from 0). capacity: length of the three arrays. */
+int carma_multi_series_get_curve(carma_multi_series_t m, size_t curve, double* time, double* y, double* yerr,
+                                 size_t capacity, size_t* ny_out);
 int carma_multi_loglik_dev(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* d_priors,
                            const double* d_theta /* ncurves x d */, double* d_logpost, unsigned flags, void* stream);
 int carma_multi_loglik(carma_multi_series_t m, int kind, int p, int q, const carma_prior_t* priors,

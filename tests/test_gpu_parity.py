@@ -589,3 +589,53 @@ def test_pt_posterior_recovers_truth_car1(C):
     ens_means = res["samples"][:, :, 3].mean(axis=1)
     assert ens_means.std() < 3 * logw.std()
     s.close()
+
+
+def test_simulated_survey_is_a_draw_from_the_model(C, O):
+    """carma_multi_series_simulate: light curves generated in HBM.  (1) reproducible and independent of how the
+    survey is sharded; (2) per-curve default priors equal the host recipe on the downloaded data; (3) K4 on the
+    resident curves equals the oracle on the downloaded ones; (4) the oracle's standardized one-step residuals
+    of the curves at theta_true are N(0,1): the generator draws from exactly the model the filter evaluates."""
+    from carma_pack_b200 import synth
+    th = synth.carma31_theta(sigmay=1.7, mu=4.0)
+    ar, ma, s2 = synth.carma31_truth()
+    nc, ny, yerr = 384, 400, 0.2
+    m = C.MultiSeries.simulate(nc, ny, C.KIND_CARMA, 3, 1, th, yerr=yerr, dt_min=0.05, dt_max=60.0, seed=11)
+    m2 = C.MultiSeries.simulate(7, ny, C.KIND_CARMA, 3, 1, th, yerr=yerr, dt_min=0.05, dt_max=60.0, seed=11, curve_offset=100)
+    for c in range(7):
+        a, b = m.curve(100 + c), m2.curve(c)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    m2.close()
+    pri = m.default_priors()
+    ts, ys, es, z_all = [], [], [], []
+    for c in range(nc):
+        t, y, e = m.curve(c)
+        dt = np.diff(t)
+        assert dt.min() >= 0.05 * (1 - 1e-9) and dt.max() <= 60.0 * (1 + 1e-9) and np.allclose(e, yerr, rtol=1e-15) and np.all(np.isfinite(y))
+        ts.append(t); ys.append(y); es.append(e)
+        op = O.default_prior(t, y)
+        assert np.allclose(tuple(pri[c]), (op.max_stdev, op.max_freq, op.min_freq, op.kappa_low, op.kappa_high, 50.0),
+                           rtol=1e-9), c
+        if c < 96:
+            mean, var = O.filterp(t, y - th[2], e, s2 * th[0] ** 2, ar, ma[:2])
+            z_all.append((y - th[2] - mean) / np.sqrt(var))
+    # Cauchy gaps: the median of dt_min + |C| is dt_min + 1
+    assert abs(np.median(np.concatenate([np.diff(t) for t in ts])) - 1.05) < 0.03
+    tcat, ycat, ecat = np.concatenate(ts), np.concatenate(ys), np.concatenate(es)
+    off = np.arange(nc + 1) * ny
+    thetas = np.tile(th, (nc, 1))
+    thetas[:, 3:] += 0.1 * np.random.default_rng(2).standard_normal((nc, 4))
+    got = m.loglik(C.KIND_CARMA, 3, 1, thetas)
+    opri = [O.default_prior(ts[c], ys[c]) for c in range(nc)]
+    want = O.logdensity_multi(O.KIND_CARMA, 3, 1, tcat, ycat, ecat, off, thetas, opri)
+    assert_logpost_parity(got, want, what="simulated survey")
+    z = np.concatenate(z_all)                       # 96 x 400 = 38,400 residuals
+    assert abs(z.mean()) < 4.0 / np.sqrt(z.size)
+    assert abs(z.var() - 1.0) < 4.0 * np.sqrt(2.0 / z.size)
+    assert abs(np.mean(z[1:] * z[:-1])) < 4.0 / np.sqrt(z.size)   # white
+    assert abs(np.mean(z ** 4) - 3.0) < 0.2                       # Gaussian tails
+    # the variance of the process is sigma_y^2 (+ noise) at theta_true
+    assert abs(np.var(ycat) / (1.7 ** 2 + yerr ** 2) - 1.0) < 0.1
+    m.close()
+    with pytest.raises(C.CarmaError):
+        C.MultiSeries.simulate(4, 1, C.KIND_CARMA, 3, 1, th)
