@@ -413,11 +413,11 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": K,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                         "traffic": 122.4e6, "traffic_source": "bytes per launch, dram__bytes_read.sum (29.8e6) + "
-                         "dram__bytes_write.sum (92.6e6), ncu --cache-control none on this command, "
-                         "profiles/r01d_k1_traffic_steady_state.csv; algorithmic bytes are 6.3e6, the excess is the "
-                         "prologue's per-thread local-memory frame (1.3 kB x 65,536 threads) written back once; "
-                         "0.29 TB/s in total on an FP64-bound kernel",
+                         "traffic": 18.85e6, "traffic_source": "bytes per launch, dram__bytes_read.sum (15.94e6) + "
+                         "dram__bytes_write.sum (2.92e6) of one ncu --set full capture of this command "
+                         "(profiles/r01j_k1_ncu_key_metrics.csv); back-to-back launches without the L2 flush move "
+                         "6-10e6 (profiles/r01j_k1_traffic_launches.csv); algorithmic bytes are 6.3e6, the rest is the "
+                         "prologue's per-thread local-memory frame (0.6 kB x 65,536 threads)",
                          "kernel": "loglik_batch_kernel<5>", "kernel_ms": kern_ms,
                          "flops_per_eval": fe, "flops_per_step_formula": "20p^2+36p+7 (SURVEY 8d), transcendentals excluded",
                          "peak_source": "DFMA saturation micro-benchmark run on this GPU in this process "

@@ -57,27 +57,30 @@ loglik_batch_kernel(SeriesView sv, int kind, int q, int d, unsigned flags, carma
         bulk_g2s(dst + chunk, sv.y + start, bytes, &bars[k & 1]);
         bulk_g2s(dst + 2 * chunk, sv.e2n + start, bytes, &bars[k & 1]);
     };
-    if (tid == 0) {
-        issue(0);
-        if (nbuf > 1) issue(1);
-    }
 
-    // ---- per-theta prologue (overlaps the copy)
+    // ---- per-theta prologue.  The P x P complex LU of the Vandermonde solve works in shared memory
+    // ([element][thread], conflict-free), in the space the series buffers take over afterwards.
     RealParams<P> prm;
     KalmanReal<P> kf;
     LogLikAcc acc;
     bool active = row < n;
     int status = TT_OK;
     if (active) {
-        double th[MAX_D];
-#pragma unroll
-        for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[row * (size_t)d + j] : 0.0;
-        status = transform_theta<P>(kind, q, flags, prior, th, prm);
+        // theta is read straight from global memory (the transform touches only its first d entries)
+        status = transform_theta<P, false, true>(kind, q, flags, prior, theta + row * (size_t)d, prm, nullptr, smem + tid,
+                                                 K1_BLOCK);
         if (status != TT_OK) active = false;
     }
     if (active) {
         kf.reset(prm, sv.e2_0);
         acc.init();
+    }
+    // the generic-proxy accesses above must be ordered before the bulk (async-proxy) writes into the same bytes
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (nbuf > 1) issue(1);
     }
 
     // ---- time loop
@@ -113,7 +116,14 @@ static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsig
     int chunk = std::min(sv.nyp, 512);
     int nchunks = (sv.ny + chunk - 1) / chunk;
     size_t smem = (size_t)(nchunks > 1 ? 2 : 1) * 3 * chunk * sizeof(double);
+    smem = std::max(smem, (size_t)2 * P * P * K1_BLOCK * sizeof(double));  // LU scratch of the prologue (aliased)
     unsigned grid = (unsigned)((n + K1_BLOCK - 1) / K1_BLOCK);
+    static bool attr_set = false;  // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 50,176 B)
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(loglik_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n, chunk);
     return cudaGetLastError();
 }

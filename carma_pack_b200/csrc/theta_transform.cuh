@@ -140,14 +140,77 @@ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
     return ok;
 }
 
+// Same elimination, same operation order (bit-identical J), with the P x P complex matrix held in shared
+// memory instead of registers: element (i,j) of the calling thread is scr[((i*P + j)*2 + {0,1}) * stride].
+// K1 uses it: 100 registers' worth of matrix no longer compete with the 128-register cap of the kernel, so the
+// prologue stops spilling ~1 kB per thread to local memory (which reached DRAM as dead write-backs).
+template <int P>
+__device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* w, cxd* J, double* scr, int stride) {
+    auto ld = [&](int i, int j) { const double* q = scr + (size_t)((i * P + j) * 2) * stride; return cxd{q[0], q[stride]}; };
+    auto st = [&](int i, int j, cxd v) { double* q = scr + (size_t)((i * P + j) * 2) * stride; q[0] = v.re; q[stride] = v.im; };
+    cxd rhs[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        cxd pw = cx(1, 0);
+        st(0, k, pw);
+#pragma unroll
+        for (int i = 1; i < P; i++) {
+            pw = pw * w[k];
+            st(i, k, pw);
+        }
+        rhs[k] = cx(k == P - 1 ? 1.0 : 0.0, 0.0);
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        int piv = k;
+        cxd akk = ld(k, k);
+        double best = fabs(akk.re) + fabs(akk.im);
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {
+            cxd a = ld(i, k);
+            double v = fabs(a.re) + fabs(a.im);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (!(best > 0.0) || !isfinite(best)) ok = false;
+        if (piv != k) {  // rows addressed at run time: free in shared memory
+#pragma unroll
+            for (int j = k; j < P; j++) { cxd a = ld(k, j), b = ld(piv, j); st(k, j, b); st(piv, j, a); }
+        }
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {  // the right-hand side stays in registers: predicated exchange
+            if (i == piv) { cxd tr = rhs[k]; rhs[k] = rhs[i]; rhs[i] = tr; }
+        }
+        akk = ld(k, k);
+#pragma unroll
+        for (int i = k + 1; i < P; i++) {
+            cxd l = cdiv(ld(i, k), akk);
+#pragma unroll
+            for (int j = k + 1; j < P; j++) st(i, j, ld(i, j) - l * ld(k, j));
+            rhs[i] = rhs[i] - l * rhs[k];
+        }
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; i--) {
+        cxd s = rhs[i];
+#pragma unroll
+        for (int j = i + 1; j < P; j++) s = s - ld(i, j) * J[j];
+        J[i] = cdiv(s, ld(i, i));
+    }
+    return ok;
+}
+
 // Returns TT_NEG_INF when the log-density is -inf (bounds violated / singular), else TT_OK.
 // __noinline__: the prologue (LU on a PxP complex matrix) gets its own register allocation, so it
 // cannot push spills into the time loop of the calling kernel.
 // Vr (optional): packed upper triangle (row-major, P(P+1)/2) of the stationary covariance in the real
 // basis, V_r = T V T^H restricted to its real part, where z = T x.  Only the scan kernels need it.
-template <int P, bool WITH_V = false>
+// lu_scratch (optional, SMEM_LU): this thread's slot of a shared-memory scratch of 2 P^2 doubles per thread,
+// laid out [element][thread] with `lu_stride` threads (see vandermonde_solve_last_smem).
+template <int P, bool WITH_V = false, bool SMEM_LU = false>
 __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
-                                            RealParams<P>& out, double* Vr = nullptr) {
+                                            RealParams<P>& out, double* Vr = nullptr, double* lu_scratch = nullptr,
+                                            int lu_stride = 0) {
     constexpr double PI = 3.14159265358979323846;
     const double ysigma = th[0], scale = th[1];
     out.scale = scale;
@@ -200,15 +263,34 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
     for (int i = 0; i < P; i++) ma[i] = (i == 0) ? 1.0 : 0.0;
     if (kind == CARMA_KIND_CARMA && q > 0) {
         cxd r[P];
-        cxd cf[P];
 #pragma unroll
-        for (int i = 0; i < P; i++) { r[i] = cx(0, 0); cf[i] = cx(0, 0); }
+        for (int i = 0; i < P; i++) r[i] = cx(0, 0);
         quad_roots_dev<P>(th + 3 + P, q, r);
-        cf[0] = cx(1.0, 0.0);
-        for (int i = 0; i < q; i++)
-            for (int j = i + 1; j >= 1; j--) cf[j] = cf[j] - r[i] * cf[j - 1];
-        double norm = cf[q].re;
-        for (int i = 0; i <= q; i++) ma[i] = cf[q - i].re / norm;
+        if (SMEM_LU) {
+            // polynomial from its roots (carpack.cpp:742-756) with the run-time-indexed coefficient array in the
+            // shared scratch (free before the LU needs it) instead of local memory
+            auto ld = [&](int j) { const double* p_ = lu_scratch + (size_t)(2 * j) * lu_stride; return cxd{p_[0], p_[lu_stride]}; };
+            auto st = [&](int j, cxd v) { double* p_ = lu_scratch + (size_t)(2 * j) * lu_stride; p_[0] = v.re; p_[lu_stride] = v.im; };
+            st(0, cx(1.0, 0.0));
+            for (int j = 1; j <= q; j++) st(j, cx(0, 0));
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                if (i < q)
+                    for (int j = i + 1; j >= 1; j--) st(j, ld(j) - r[i] * ld(j - 1));
+            const double norm = ld(q).re;
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                if (i <= q) ma[i] = ld(q - i).re / norm;
+        } else {
+            cxd cf[P];
+#pragma unroll
+            for (int i = 0; i < P; i++) cf[i] = cx(0, 0);
+            cf[0] = cx(1.0, 0.0);
+            for (int i = 0; i < q; i++)
+                for (int j = i + 1; j >= 1; j--) cf[j] = cf[j] - r[i] * cf[j - 1];
+            double norm = cf[q].re;
+            for (int i = 0; i <= q; i++) ma[i] = cf[q - i].re / norm;
+        }
     } else if (kind == CARMA_KIND_ZCARMA) {
         double x = th[3 + P];
         double kn = exp(x) / (1.0 + exp(x));
@@ -253,7 +335,10 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
     // i.e. exact for slightly perturbed roots, and the massive cancellation in b V b^H for clustered
     // roots is benign under such consistent perturbations while it amplifies independent ones.)
     cxd J[P];
-    if (!vandermonde_solve_last<P>(w, J)) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
+    bool solved;
+    if (SMEM_LU) solved = vandermonde_solve_last_smem<P>(w, J, lu_scratch, lu_stride);
+    else solved = vandermonde_solve_last<P>(w, J);
+    if (!solved) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
 
     // ---- stationary covariance V (kfilter.cpp:165-172), h = V b^H, v0 = Re(b V b^H)
     cxd h[P];
