@@ -645,3 +645,41 @@ def test_simulated_survey_is_a_draw_from_the_model(C, O):
     m.close()
     with pytest.raises(C.CarmaError):
         C.MultiSeries.simulate(4, 1, C.KIND_CARMA, 3, 1, th)
+
+
+def test_simulated_survey_other_model_kinds(C, O):
+    """The generator for CAR(1) and for a real-root CAR(4) (generic transition blocks): the K4 log-likelihood of the
+    simulated curves at theta_true equals the oracle's, and its standardized residuals are N(0,1)."""
+    # CAR(1): theta = (sigma_y, measerr_scale, mu, log omega)
+    sig_y, mu, omega, yerr = 1.3, -2.0, 0.08, 0.1
+    th = np.array([sig_y, 1.0, mu, np.log(omega)])
+    m = C.MultiSeries.simulate(128, 300, C.KIND_CAR1, 1, 0, th, yerr=yerr, dt_min=0.2, dt_max=40.0, seed=5)
+    zs = []
+    for c in range(128):
+        t, y, e = m.curve(c)
+        mean, var = O.filter1(t, y - mu, e, 2.0 * sig_y ** 2 * omega, omega)
+        zs.append((y - mu - mean) / np.sqrt(var))
+    z = np.concatenate(zs)
+    assert abs(z.mean()) < 4.0 / np.sqrt(z.size) and abs(z.var() - 1.0) < 4.0 * np.sqrt(2.0 / z.size)
+    m.close()
+    # CAR(4) with two overdamped (real-root) quadratic factors
+    th4 = np.array([0.9, 1.0, 1.0, np.log(0.02), np.log(0.9), np.log(0.5), np.log(3.0)])
+    m = C.MultiSeries.simulate(96, 250, C.KIND_CARP, 4, 0, th4, yerr=0.05, dt_min=0.1, dt_max=30.0, seed=6)
+    ts, ys, es = zip(*[m.curve(c) for c in range(96)])
+    off = np.arange(97) * 250
+    thetas = np.tile(th4, (96, 1))
+    got = m.loglik(C.KIND_CARP, 4, 0, thetas, flags=C.IGNORE_BOUNDS)
+    opri = [O.default_prior(ts[c], ys[c]) for c in range(96)]
+    want = O.logdensity_multi(O.KIND_CARP, 4, 0, np.concatenate(ts), np.concatenate(ys), np.concatenate(es), off, thetas,
+                              opri, ignore_prior=True)
+    assert_logpost_parity(got, want, rtol=1e-8, what="simulated CAR(4)")
+    # -2 loglik + sum log var = chi^2 with ny dof per curve: the mean over curves of the quadratic form is ny
+    roots = O.ar_roots(th4[3:7])
+    sig2 = th4[0] ** 2 / O.variance(roots, np.array([1.0, 0.0, 0.0, 0.0]))
+    chi2 = []
+    for c in range(96):
+        mean, var = O.filterp(ts[c], ys[c] - th4[2], es[c], sig2, roots, [1.0])
+        chi2.append(np.sum((ys[c] - th4[2] - mean) ** 2 / var))
+    chi2 = np.array(chi2)
+    assert abs(chi2.mean() / 250.0 - 1.0) < 4.0 * np.sqrt(2.0 / (250.0 * 96.0))
+    m.close()
