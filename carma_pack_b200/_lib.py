@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
     "carma_multi_series_simulate", "carma_multi_series_get_curve",
+    "carma_mle_default_opts", "carma_mle_batch",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
@@ -52,6 +53,12 @@ class PTOpts(ctypes.Structure):
                 ("target_rate", ctypes.c_double), ("gamma", ctypes.c_double), ("seed", ctypes.c_uint64),
                 ("ensemble_offset", ctypes.c_uint32), ("max_start_attempts", ctypes.c_int),
                 ("order_mode", ctypes.c_int), ("record_trace", ctypes.c_int)]
+
+
+class MLEOpts(ctypes.Structure):
+    _fields_ = [("maxiter", ctypes.c_int), ("history", ctypes.c_int), ("max_backtrack", ctypes.c_int),
+                ("reserved", ctypes.c_int), ("gtol", ctypes.c_double), ("ftol", ctypes.c_double),
+                ("fd_eps", ctypes.c_double)]
 
 
 TRACE_DTYPE = np.dtype([("lp_prop", "f8"), ("lp_cur", "f8"), ("alpha", "f8"), ("u", "f8"),
@@ -93,6 +100,11 @@ def _load():
                                               ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
                                               ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(_vp)]
     L.carma_multi_series_get_curve.argtypes = [_vp, _sz, _dp, _dp, _dp, _sz, ctypes.POINTER(_sz)]
+    L.carma_mle_default_opts.argtypes = [ctypes.POINTER(MLEOpts)]
+    L.carma_mle_default_opts.restype = None
+    L.carma_mle_batch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.c_uint, _sz, _dp, _dp, _dp,
+                                  ctypes.POINTER(MLEOpts), _dp, _dp, ctypes.POINTER(ctypes.c_int),
+                                  ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     L.carma_multi_loglik_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
                                          ctypes.c_uint, _vp]
     L.carma_multi_loglik.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_uint]
@@ -280,6 +292,28 @@ class Series:
         if record_trace:
             res.update(ram_trace=rt, exchange_trace=xt, proposals=prop)
         return res
+
+    def mle_batch(self, kind, p, q, x0, lower, upper, prior=None, flags=0, maxiter=200, history=8, gtol=1e-5,
+                  ftol=2.2e-9, fd_eps=1e-8, slot=0):
+        """Projected L-BFGS from every row of x0 in lock-step (carma_mle_batch): minimises -LogDensity over the
+        box [lower, upper].  Returns (x, f, nit, nfev).  Releases the GIL for the whole fit."""
+        d = model_dim(kind, p, q)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if x0.ndim != 2 or x0.shape[1] != d:
+            raise ValueError("x0 must be (nstart, %d)" % d)
+        lo, hi = _c(np.broadcast_to(lower, (d,))), _c(np.broadcast_to(upper, (d,)))
+        if prior is None:
+            prior = self.default_prior()
+        o = MLEOpts()
+        lib.carma_mle_default_opts(ctypes.byref(o))
+        o.maxiter, o.history, o.gtol, o.ftol, o.fd_eps = int(maxiter), int(history), gtol, ftol, fd_eps
+        n = x0.shape[0]
+        x, f = np.empty((n, d)), np.empty(n)
+        nit, nfev = ctypes.c_int(0), ctypes.c_longlong(0)
+        check(lib.carma_mle_batch(self.handle, kind, p, q, ctypes.byref(prior), flags, n, _ptr(x0), _ptr(lo), _ptr(hi),
+                                  ctypes.byref(o), _ptr(x), _ptr(f), ctypes.byref(nit), ctypes.byref(nfev), slot),
+              "carma_mle_batch")
+        return x, f, nit.value, nfev.value
 
     def pt_run_dev(self, kind, p, q, opts, n_ensembles, d_samples, d_logposts, prior, d_init=None, d_accept=None,
                    d_exchange=None, stream=0):

@@ -205,11 +205,14 @@ class CarmaModel(object):
             hi += [np.inf] * q
         return np.array(lo), np.array(hi)
 
-    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0, series=None):
+    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0, series=None,
+                optimizer="native"):
         """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
         in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
         global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
-        rank runs it).  series: device series to use (choose_order gives each worker thread its own)."""
+        rank runs it).  series: device series to use (choose_order gives each worker thread its own).
+        optimizer: "native" = carma_mle_batch (C++ host loop, no interpreter in the iteration);
+        "python" = the same algorithm in numpy (batched_lbfgs), kept as the cross-check."""
         series = self.series if series is None else series
         kind = _kind_for(p, q)
         d = model_dim(kind, p, q)
@@ -237,7 +240,12 @@ class CarmaModel(object):
             series.loglik_wait(0)
             return -out
 
-        x, f, nit, nfev = batched_lbfgs(negloglik, x0, lo, hi, maxiter=maxiter)
+        if optimizer == "native":
+            x, f, nit, nfev = series.mle_batch(kind, p, q, x0, lo, hi, prior=prior, flags=flags, maxiter=maxiter)
+        elif optimizer == "python":
+            x, f, nit, nfev = batched_lbfgs(negloglik, x0, lo, hi, maxiter=maxiter)
+        else:
+            raise ValueError("optimizer must be 'native' or 'python'")
         best = int(np.argmin(f))
         mle = OptimizeResult(x=x[best], fun=float(f[best]), nit=nit, nfev=nfev, success=bool(np.isfinite(f[best])),
                              message="batched projected L-BFGS, best of %d starts" % ntrials,
@@ -276,7 +284,7 @@ class CarmaModel(object):
         # (own scratch buffers and stream), so their launches overlap on the GPU.  Heaviest models first.
         from concurrent.futures import ThreadPoolExecutor
         units.sort(key=lambda u: -(pqlist[u[0]][0] ** 2) * (4 + sum(pqlist[u[0]])) * u[2])
-        nworkers = max(1, min(8, len(units)))
+        nworkers = max(1, min(32, len(units)))  # the fits release the GIL: host threads only marshal launches
         pool_series = [Series(self.time, self.y, self.ysig, device=self.device) for _ in range(nworkers)]
         import queue
         free = queue.Queue()

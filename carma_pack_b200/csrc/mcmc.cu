@@ -37,6 +37,7 @@
 namespace carma {
 
 constexpr int PT_BLOCK = 64;
+constexpr size_t PT_SMEM_MAX = 96 * 1024;  // series resident in shared memory up to this size
 
 struct PTParams {
     int kind, q, d;
@@ -455,7 +456,10 @@ template <int P>
 static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t chol_stride, unsigned grid,
                              cudaStream_t stream, const PTMulti& mm) {
     size_t smem = pt_smem_bytes(mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0, pp.d);
-    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the same value (the residency rule keeps smem <= PT_SMEM_MAX): function attributes are process-wide,
+    // and fits of different models launch this kernel concurrently from several host threads
+    if (smem > PT_SMEM_MAX) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX);
     if (e != cudaSuccess) return e;
     pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
     return cudaGetLastError();
@@ -547,7 +551,7 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         scratch = &m->scratch_misc;
     }
     // series resident in shared memory when it fits (<= 96 KiB keeps at least two blocks per SM)
-    mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= 96 * 1024 ? 1 : 0;
+    mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= PT_SMEM_MAX ? 1 : 0;
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
     if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;

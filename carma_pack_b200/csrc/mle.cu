@@ -1,0 +1,296 @@
+// mle.cu -- maximum-likelihood fits from many random starts, all starts in lock-step (host code).
+//
+// Replaces the per-start scipy.optimize.minimize(method="L-BFGS-B") calls of the reference's
+// _get_mle_single (src/carmcmc/carma_pack.py:195-252, objective _carma_loglik 255-260: one FFI crossing and one
+// full filter run per function value, 2(d)+1 of them per finite-difference gradient).  Here every iteration of
+// the optimiser is a handful of batched K1 launches over all starts: n*d perturbed points for the forward-
+// difference gradients, n candidate points per backtracking step.  The host side of an iteration is O(n m d)
+// flops in plain loops; it runs outside the Python interpreter, so fits of different (p,q) models driven from
+// different host threads overlap on the GPU (each through its own series handle and stream slot).
+//
+// Algorithm: projected L-BFGS (two-loop recursion, history m) with forward-difference gradients (scipy's
+// epsilon = 1e-8, stepping inward at an upper bound), Armijo backtracking along the projected path, stop on
+// projected-gradient norm < gtol or relative decrease <= ftol (L-BFGS-B's factr*epsmch = 2.2e-9).  It is the
+// C++ twin of carma_pack_b200.carma_pack.batched_lbfgs, which the tests keep as the cross-check.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "series.h"
+#include "theta_transform.cuh"
+
+using namespace carma;
+
+extern "C" void carma_mle_default_opts(carma_mle_opts_t* o) {
+    if (!o) return;
+    o->maxiter = 200;
+    o->history = 8;
+    o->max_backtrack = 25;
+    o->reserved = 0;
+    o->gtol = 1e-5;
+    o->ftol = 2.2e-9;
+    o->fd_eps = 1e-8;
+}
+
+namespace {
+
+constexpr double BIG = 1e300;
+
+struct PinnedBuf {
+    double* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (cudaHostAlloc((void**)&p, n * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return false; }
+        cap = n;
+        return true;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+
+struct Evaluator {
+    carma_series_t s;
+    int kind, p, q, slot;
+    const carma_prior_t* prior;
+    unsigned flags;
+    size_t d;
+    PinnedBuf in, out;
+    long long nfev = 0;
+    // f[k] = -LogDensity(theta_k) for k < n; non-finite -> BIG.  theta rows are already in in.p.
+    int run(size_t n, double* f) {
+        if (n == 0) return CARMA_OK;
+        int rc = carma_loglik_batch_async(s, kind, p, q, prior, n, in.p, out.p, flags, slot);
+        if (rc) return rc;
+        rc = carma_loglik_batch_wait(s, slot);
+        if (rc) return rc;
+        for (size_t k = 0; k < n; k++) {
+            double v = -out.p[k];
+            f[k] = std::isfinite(v) ? v : BIG;
+        }
+        nfev += (long long)n;
+        return CARMA_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
+                               size_t nstart, const double* x0, const double* lower, const double* upper,
+                               const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out,
+                               long long* nfev_out, int slot) {
+    if (!s || !prior || !x0 || !lower || !upper || !x_out || !f_out || slot < 0 || slot > 1) {
+        set_error("carma_mle_batch: bad argument");
+        return CARMA_ERR_ARG;
+    }
+    if (kind < CARMA_KIND_CAR1 || kind > CARMA_KIND_ZCARMA || p < 1 || p > MAX_P || (kind == CARMA_KIND_CAR1 && p != 1) ||
+        (kind == CARMA_KIND_CARMA && !(q >= 0 && q < p))) {
+        set_error("carma_mle_batch: invalid (kind,p,q)");
+        return CARMA_ERR_ARG;
+    }
+    carma_mle_opts_t o;
+    if (opts) o = *opts; else carma_mle_default_opts(&o);
+    if (o.maxiter < 0 || o.history < 1 || o.history > 64 || o.max_backtrack < 1 || !(o.fd_eps > 0)) {
+        set_error("carma_mle_batch: invalid options");
+        return CARMA_ERR_ARG;
+    }
+    if (nit_out) *nit_out = 0;
+    if (nfev_out) *nfev_out = 0;
+    if (nstart == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+
+    const size_t n = nstart, d = (size_t)model_dim(kind, p, q);
+    const int m = o.history;
+    Evaluator ev{s, kind, p, q, slot, prior, flags, d};
+    if (!ev.in.reserve(n * d * d) || !ev.out.reserve(n * d)) { set_error("carma_mle_batch: pinned allocation failed"); return CARMA_ERR_ALLOC; }
+
+    std::vector<double> x(n * d), f(n), g(n * d), xn(n * d), fn(n), gn(n * d), pg(n * d), qv(n * d), dir(n * d), slope(n), t(n);
+    std::vector<double> S((size_t)m * n * d), Y((size_t)m * n * d), alpha((size_t)m * n), rho((size_t)m * n), ftmp(n * d);
+    std::vector<char> active(n), todo(n), moved(n), blocked(n * d);
+    std::vector<size_t> rows;
+    int nhist = 0;  // history entries in use; entry h lives at slot (hist0 + h) % m, oldest first
+    int hist0 = 0;
+
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < d; j++) x[i * d + j] = std::min(std::max(x0[i * d + j], lower[j]), upper[j]);
+
+    // forward-difference gradients of the listed rows at (z, fz) -> gout
+    auto grad = [&](const std::vector<size_t>& rr, const std::vector<double>& z, const std::vector<double>& fz,
+                    std::vector<double>& gout) -> int {
+        size_t k = 0;
+        for (size_t i : rr)
+            for (size_t j = 0; j < d; j++, k++) {
+                std::memcpy(ev.in.p + k * d, &z[i * d], d * sizeof(double));
+                double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+                ev.in.p[k * d + j] += h;
+            }
+        int rc = ev.run(k, ftmp.data());
+        if (rc) return rc;
+        k = 0;
+        for (size_t i : rr)
+            for (size_t j = 0; j < d; j++, k++) {
+                double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+                gout[i * d + j] = (std::fabs(ftmp[k]) >= BIG) ? 0.0 : (ftmp[k] - fz[i]) / h;
+            }
+        return CARMA_OK;
+    };
+
+    std::memcpy(ev.in.p, x.data(), n * d * sizeof(double));
+    int rc = ev.run(n, f.data());
+    if (rc) return rc;
+    rows.resize(n);
+    for (size_t i = 0; i < n; i++) rows[i] = i;
+    rc = grad(rows, x, f, g);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) active[i] = f[i] < BIG;
+
+    int nit = 0;
+    for (nit = 1; nit <= o.maxiter; nit++) {
+        // projected gradient: zero the components pushing against an active bound
+        bool any_active = false;
+        for (size_t i = 0; i < n; i++) {
+            double gmax = 0.0;
+            for (size_t j = 0; j < d; j++) {
+                const double xi = x[i * d + j], gi = g[i * d + j];
+                const bool blk = (xi <= lower[j] && gi > 0) || (xi >= upper[j] && gi < 0);
+                blocked[i * d + j] = blk;
+                pg[i * d + j] = blk ? 0.0 : gi;
+                gmax = std::max(gmax, std::fabs(pg[i * d + j]));
+            }
+            if (gmax < o.gtol) active[i] = 0;
+            any_active = any_active || active[i];
+        }
+        if (!any_active) break;
+        // two-loop recursion, row by row
+        for (size_t i = 0; i < n; i++) {
+            double* qi = &qv[i * d];
+            const double* pgi = &pg[i * d];
+            for (size_t j = 0; j < d; j++) qi[j] = pgi[j];
+            for (int h = nhist - 1; h >= 0; h--) {
+                const size_t sl = (size_t)((hist0 + h) % m);
+                const double *sv = &S[(sl * n + i) * d], *yv = &Y[(sl * n + i) * d];
+                double sy = 0.0, sq = 0.0;
+                for (size_t j = 0; j < d; j++) { sy += sv[j] * yv[j]; sq += sv[j] * qi[j]; }
+                const double r = 1.0 / std::max(sy, 1e-300), a = r * sq;
+                rho[sl * n + i] = r;
+                alpha[sl * n + i] = a;
+                for (size_t j = 0; j < d; j++) qi[j] -= a * yv[j];
+            }
+            if (nhist > 0) {
+                const size_t sl = (size_t)((hist0 + nhist - 1) % m);
+                const double *sv = &S[(sl * n + i) * d], *yv = &Y[(sl * n + i) * d];
+                double sy = 0.0, yy = 0.0;
+                for (size_t j = 0; j < d; j++) { sy += sv[j] * yv[j]; yy += yv[j] * yv[j]; }
+                const double gam = std::min(std::max(sy / std::max(yy, 1e-300), 1e-8), 1e8);
+                for (size_t j = 0; j < d; j++) qi[j] *= gam;
+            } else {
+                double nrm = 0.0;
+                for (size_t j = 0; j < d; j++) nrm += pgi[j] * pgi[j];
+                const double sc = 1.0 / std::max(std::sqrt(nrm), 1.0);
+                for (size_t j = 0; j < d; j++) qi[j] *= sc;
+            }
+            for (int h = 0; h < nhist; h++) {
+                const size_t sl = (size_t)((hist0 + h) % m);
+                const double *sv = &S[(sl * n + i) * d], *yv = &Y[(sl * n + i) * d];
+                double yq = 0.0;
+                for (size_t j = 0; j < d; j++) yq += yv[j] * qi[j];
+                const double b = rho[sl * n + i] * yq, a = alpha[sl * n + i];
+                for (size_t j = 0; j < d; j++) qi[j] += (a - b) * sv[j];
+            }
+            double sl_ = 0.0, pg2 = 0.0;
+            for (size_t j = 0; j < d; j++) {
+                dir[i * d + j] = blocked[i * d + j] ? 0.0 : -qi[j];
+                sl_ += dir[i * d + j] * pgi[j];
+                pg2 += pgi[j] * pgi[j];
+            }
+            if (!(sl_ < 0)) {
+                for (size_t j = 0; j < d; j++) dir[i * d + j] = -pgi[j];
+                sl_ = -pg2;
+            }
+            slope[i] = sl_;
+        }
+        // batched Armijo backtracking on the projected path (only the rows still searching are evaluated)
+        for (size_t i = 0; i < n; i++) { t[i] = 1.0; todo[i] = active[i]; fn[i] = f[i]; }
+        xn = x;
+        for (int bt = 0; bt < o.max_backtrack; bt++) {
+            rows.clear();
+            for (size_t i = 0; i < n; i++) if (todo[i]) rows.push_back(i);
+            if (rows.empty()) break;
+            size_t k = 0;
+            for (size_t i : rows) {
+                for (size_t j = 0; j < d; j++)
+                    ev.in.p[k * d + j] = std::min(std::max(x[i * d + j] + t[i] * dir[i * d + j], lower[j]), upper[j]);
+                k++;
+            }
+            rc = ev.run(k, ftmp.data());
+            if (rc) return rc;
+            k = 0;
+            for (size_t i : rows) {
+                if (ftmp[k] <= f[i] + 1e-4 * t[i] * slope[i]) {
+                    std::memcpy(&xn[i * d], ev.in.p + k * d, d * sizeof(double));
+                    fn[i] = ftmp[k];
+                    todo[i] = 0;
+                } else {
+                    t[i] *= 0.5;
+                }
+                k++;
+            }
+        }
+        rows.clear();
+        for (size_t i = 0; i < n; i++) {
+            moved[i] = active[i] && !todo[i];
+            if (moved[i]) rows.push_back(i);
+        }
+        gn = g;
+        if (!rows.empty()) {
+            rc = grad(rows, xn, fn, gn);
+            if (rc) return rc;
+        }
+        // history update: rows without positive curvature contribute zero vectors
+        bool any_curv = false;
+        const size_t slnew = (size_t)((hist0 + nhist) % m);  // slot that would receive the new pair
+        std::vector<double>& Sn = ftmp;                        // reuse as scratch of size n*d for s; y goes to qv
+        for (size_t i = 0; i < n; i++) {
+            double sy = 0.0;
+            for (size_t j = 0; j < d; j++) {
+                const double sv = moved[i] ? xn[i * d + j] - x[i * d + j] : 0.0;
+                const double yv = moved[i] ? gn[i * d + j] - g[i * d + j] : 0.0;
+                Sn[i * d + j] = sv;
+                qv[i * d + j] = yv;
+                sy += sv * yv;
+            }
+            const bool curv = sy > 1e-12;
+            any_curv = any_curv || curv;
+            if (!curv)
+                for (size_t j = 0; j < d; j++) { Sn[i * d + j] = 0.0; qv[i * d + j] = 0.0; }
+        }
+        if (any_curv) {
+            size_t dst = slnew;
+            if (nhist == m) {  // drop the oldest
+                dst = (size_t)hist0;
+                hist0 = (hist0 + 1) % m;
+            } else {
+                nhist++;
+            }
+            std::memcpy(&S[dst * n * d], Sn.data(), n * d * sizeof(double));
+            std::memcpy(&Y[dst * n * d], qv.data(), n * d * sizeof(double));
+        }
+        for (size_t i = 0; i < n; i++) {
+            const bool small = moved[i] && ((f[i] - fn[i]) <= o.ftol * std::max(std::max(std::fabs(f[i]), std::fabs(fn[i])), 1.0));
+            if (todo[i]) active[i] = 0;  // line search failed: stop that row
+            if (small) active[i] = 0;
+        }
+        x = xn;
+        f = fn;
+        g = gn;
+    }
+    std::memcpy(x_out, x.data(), n * d * sizeof(double));
+    std::memcpy(f_out, f.data(), n * sizeof(double));
+    if (nit_out) *nit_out = std::min(nit, o.maxiter);
+    if (nfev_out) *nfev_out = ev.nfev;
+    return CARMA_OK;
+}

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CARMA_B200_ABI_VERSION 1
+#define CARMA_B200_ABI_VERSION 2
 
 enum {
     CARMA_OK = 0,
@@ -117,6 +117,29 @@ int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const car
 int carma_loglik_batch_wait(carma_series_t s, int slot);
 /* CARMA_Base::getLogPrior (src/include/carpack.hpp:221-225): host-side scalar helper. */
 int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out);
+
+/* ---- maximum-likelihood fits from many starts ----------------------------------------------
+ * Replaces the ntrials scipy L-BFGS-B runs of CarmaModel.get_mle / _get_mle_single / _carma_loglik
+ * (src/carmcmc/carma_pack.py:92-129, 195-260): projected L-BFGS with forward-difference gradients over a box,
+ * all nstart starts in lock-step, every function value of an iteration evaluated in one batched launch.
+ * The objective is  -LogDensity(theta)  with `flags` (CARMA_IGNORE_BOUNDS = SetMLE(true), carma_pack.py:242).
+ * lower/upper: d entries, +-infinity allowed.  Outputs: x_out[nstart][d], f_out[nstart] (1e300 where no finite
+ * value was ever found); nit_out / nfev_out may be NULL.  slot: the stream slot of the series to use (0/1), so
+ * fits driven from different host threads on different series handles overlap on the GPU. */
+typedef struct carma_mle_opts {
+    int maxiter;        /* 200 */
+    int history;        /* L-BFGS pairs kept, 8 */
+    int max_backtrack;  /* Armijo halvings per iteration, 25 */
+    int reserved;
+    double gtol;        /* projected-gradient infinity norm, 1e-5 (scipy pgtol) */
+    double ftol;        /* relative decrease, 2.2e-9 (scipy factr * eps) */
+    double fd_eps;      /* forward-difference step, 1e-8 (scipy approx_grad epsilon) */
+} carma_mle_opts_t;
+void carma_mle_default_opts(carma_mle_opts_t* o);
+int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
+                    size_t nstart, const double* x0, const double* lower, const double* upper,
+                    const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out, long long* nfev_out,
+                    int slot);
 
 /* ---- multi light-curve batch (one theta per curve) ----------------------------------------
  * The reference loops over objects in Python; this is the survey-scale form of the same

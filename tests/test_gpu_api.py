@@ -243,3 +243,31 @@ def test_simulate_is_conditional_draw(cm, kelly):
     # the filter object is restored afterwards
     kf.Filter()
     np.testing.assert_allclose(np.array(kf.GetVar()), kelly["var"][:n], rtol=1e-9)
+
+
+def test_native_optimizer_matches_numpy_twin(cm):
+    """carma_mle_batch (C++ host loop) against batched_lbfgs (numpy) from the same starts: same algorithm, so the
+    best optimum agrees closely and the per-start optima agree for the large majority of starts (summation order
+    differs, and forward-difference gradients amplify that on flat directions)."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(200, 11)
+    model = cm.CarmaModel(t, y, e)
+    for p, q in ((1, 0), (3, 1), (5, 2)):
+        a = model.get_mle(p, q, ntrials=32, seed=21, optimizer="native")
+        b = model.get_mle(p, q, ntrials=32, seed=21, optimizer="python")
+        assert np.isfinite(a.fun) and np.isfinite(b.fun)
+        assert abs(a.fun - b.fun) < 1e-3 * max(1.0, abs(b.fun)), (p, q, a.fun, b.fun)
+        fa, fb = np.asarray(a.all_fun), np.asarray(b.all_fun)
+        both = (fa < 1e299) & (fb < 1e299)
+        assert both.sum() >= 24
+        close = np.abs(fa[both] - fb[both]) < 1e-2 * np.maximum(1.0, np.abs(fb[both]))
+        assert close.mean() > 0.7, (p, q, close.mean())
+        # every native optimum is a genuine function value: re-evaluate it
+        kind = cm.KIND_CAR1 if p == 1 else (cm.KIND_CARMA if q > 0 else cm.KIND_CARP)
+        flags = 0 if p == 1 else cm.IGNORE_BOUNDS
+        re = -model.series.loglik(kind, p, q, a.all_x[both], prior=model.series.default_prior(True), flags=flags)
+        np.testing.assert_allclose(re, fa[both], rtol=1e-12)
+        assert a.nfev > 0 and a.nit >= 1
+    # argument checking
+    with pytest.raises(cm.CarmaError):
+        model.series.mle_batch(cm.KIND_CARMA, 3, 1, np.zeros((2, 7)), -np.ones(7), np.ones(7), slot=5)
