@@ -284,7 +284,10 @@ class CarmaModel(object):
         # (own scratch buffers and stream), so their launches overlap on the GPU.  Heaviest models first.
         from concurrent.futures import ThreadPoolExecutor
         units.sort(key=lambda u: -(pqlist[u[0]][0] ** 2) * (4 + sum(pqlist[u[0]])) * u[2])
-        nworkers = max(1, min(32, len(units)))  # the fits release the GIL: host threads only marshal launches
+        # the fits release the GIL; each worker spins in a stream synchronise while its launch runs, so more
+        # workers than host cores only add contention
+        import os
+        nworkers = max(1, min(len(units), max(4, min(16, os.cpu_count() or 8))))
         pool_series = [Series(self.time, self.y, self.ysig, device=self.device) for _ in range(nworkers)]
         import queue
         free = queue.Queue()

@@ -593,6 +593,10 @@ int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* 
     if (rc) return rc;
     if (n_ensembles == 0) return CARMA_OK;
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    // the run lives on the series' own non-blocking stream: runs driven from different host threads on different
+    // series handles (choose_order) overlap instead of queueing on the default stream
+    if (!s->slot_stream[1] && !cuda_ok(cudaStreamCreateWithFlags(&s->slot_stream[1], cudaStreamNonBlocking), "cudaStreamCreate")) return CARMA_ERR_CUDA;
+    cudaStream_t st = s->slot_stream[1];
     const bool rec = o->record_trace && ram_trace && exch_trace && proposals;
     const size_t d = (size_t)model_dim(kind, p, q), T = (size_t)o->ntemps;
     const size_t iters = (size_t)o->burnin + (size_t)o->nsamples * o->thin;
@@ -608,29 +612,30 @@ int carma_pt_run(carma_series_t s, int kind, int p, int q, const carma_prior_t* 
     carma_pt_trace_rec_t* d_rt = (carma_pt_trace_rec_t*)(d_xr + n_ensembles * T);
     carma_pt_trace_rec_t* d_xt = d_rt + n_tr;
     double* d_pr = (double*)(d_xt + n_tr);
-    if (!cuda_ok(cudaMemset(s->scratch_out.p, 0, bytes_out + bytes_tr), "memset outputs")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemsetAsync(s->scratch_out.p, 0, bytes_out + bytes_tr, st), "memset outputs")) return CARMA_ERR_CUDA;
     const double* d_init = nullptr;
     if (init) {
-        if (!cuda_ok(cudaMemcpy(s->scratch_in.p, init, d * sizeof(double), cudaMemcpyHostToDevice), "H2D init")) return CARMA_ERR_CUDA;
+        if (!cuda_ok(cudaMemcpyAsync(s->scratch_in.p, init, d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D init")) return CARMA_ERR_CUDA;
         d_init = (const double*)s->scratch_in.p;
     }
     int* d_status = nullptr;
     rc = pt_launch(s, nullptr, nullptr, kind, p, q, prior, o, n_ensembles, d_init, d_samples, d_lp, d_ar, d_xr,
-                   rec ? d_rt : nullptr, rec ? d_xt : nullptr, rec ? d_pr : nullptr, 0, &d_status);
+                   rec ? d_rt : nullptr, rec ? d_xt : nullptr, rec ? d_pr : nullptr, st, &d_status);
     if (rc) return rc;
-    if (!cuda_ok(cudaDeviceSynchronize(), "pt_kernel")) return CARMA_ERR_CUDA;
     int status = 0;
-    if (!cuda_ok(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost), "D2H status")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st), "D2H status")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaStreamSynchronize(st), "pt_kernel")) return CARMA_ERR_CUDA;
     if (status) { set_error("carma_pt_run: a chain found no finite starting value within max_start_attempts"); return CARMA_ERR_START; }
-    bool ok = cuda_ok(cudaMemcpy(samples, d_samples, n_s * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H samples") &&
-              cuda_ok(cudaMemcpy(logposts, d_lp, n_s * sizeof(double), cudaMemcpyDeviceToHost), "D2H logposts");
-    if (ok && accept_rates) ok = cuda_ok(cudaMemcpy(accept_rates, d_ar, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H accept");
-    if (ok && exchange_rates) ok = cuda_ok(cudaMemcpy(exchange_rates, d_xr, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost), "D2H exch");
+    bool ok = cuda_ok(cudaMemcpyAsync(samples, d_samples, n_s * d * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H samples") &&
+              cuda_ok(cudaMemcpyAsync(logposts, d_lp, n_s * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logposts");
+    if (ok && accept_rates) ok = cuda_ok(cudaMemcpyAsync(accept_rates, d_ar, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H accept");
+    if (ok && exchange_rates) ok = cuda_ok(cudaMemcpyAsync(exchange_rates, d_xr, n_ensembles * T * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H exch");
     if (ok && rec) {
-        ok = cuda_ok(cudaMemcpy(ram_trace, d_rt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost), "D2H ram trace") &&
-             cuda_ok(cudaMemcpy(exch_trace, d_xt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost), "D2H exch trace") &&
-             cuda_ok(cudaMemcpy(proposals, d_pr, n_tr * d * sizeof(double), cudaMemcpyDeviceToHost), "D2H proposals");
+        ok = cuda_ok(cudaMemcpyAsync(ram_trace, d_rt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost, st), "D2H ram trace") &&
+             cuda_ok(cudaMemcpyAsync(exch_trace, d_xt, n_tr * sizeof(carma_pt_trace_rec_t), cudaMemcpyDeviceToHost, st), "D2H exch trace") &&
+             cuda_ok(cudaMemcpyAsync(proposals, d_pr, n_tr * d * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H proposals");
     }
+    if (ok) ok = cuda_ok(cudaStreamSynchronize(st), "pt_run D2H");
     return ok ? CARMA_OK : CARMA_ERR_CUDA;
 }
 
