@@ -118,11 +118,11 @@ static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsig
     size_t smem = (size_t)(nchunks > 1 ? 2 : 1) * 3 * chunk * sizeof(double);
     smem = std::max(smem, (size_t)2 * P * P * K1_BLOCK * sizeof(double));  // LU scratch of the prologue (aliased)
     unsigned grid = (unsigned)((n + K1_BLOCK - 1) / K1_BLOCK);
-    static bool attr_set = false;  // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 50,176 B)
-    if (!attr_set) {
+    if (smem > 48 * 1024) {
+        // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 50,176 B).  Per device and always the same
+        // value, so concurrent callers cannot disagree.
         cudaError_t e = cudaFuncSetAttribute(loglik_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n, chunk);
     return cudaGetLastError();

@@ -106,11 +106,12 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
     const size_t n = nstart, d = (size_t)model_dim(kind, p, q);
     const int m = o.history;
     Evaluator ev{s, kind, p, q, slot, prior, flags, d};
-    if (!ev.in.reserve(n * d * d) || !ev.out.reserve(n * d)) { set_error("carma_mle_batch: pinned allocation failed"); return CARMA_ERR_ALLOC; }
+    if (!ev.in.reserve(n * (d + 4) * d) || !ev.out.reserve(n * (d + 4))) { set_error("carma_mle_batch: pinned allocation failed"); return CARMA_ERR_ALLOC; }
 
     std::vector<double> x(n * d), f(n), g(n * d), xn(n * d), fn(n), gn(n * d), pg(n * d), qv(n * d), dir(n * d), slope(n), t(n);
     std::vector<double> S((size_t)m * n * d), Y((size_t)m * n * d), alpha((size_t)m * n), rho((size_t)m * n), ftmp(n * d);
-    std::vector<char> active(n), todo(n), moved(n), blocked(n * d);
+    std::vector<char> active(n), todo(n), moved(n), blocked(n * d), grad_done(n);
+    std::vector<double> fbig(n * (d + 4));
     std::vector<size_t> rows;
     int nhist = 0;  // history entries in use; entry h lives at slot (hist0 + h) % m, oldest first
     int hist0 = 0;
@@ -213,39 +214,71 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
             }
             slope[i] = sl_;
         }
-        // batched Armijo backtracking on the projected path (only the rows still searching are evaluated)
-        for (size_t i = 0; i < n; i++) { t[i] = 1.0; todo[i] = active[i]; fn[i] = f[i]; }
+        // batched Armijo backtracking on the projected path.  The step sizes are tried in the usual order
+        // 1, 1/2, 1/4, ... and the first one that satisfies the condition is taken, but FOUR consecutive sizes of
+        // every row still searching are evaluated per launch, and the first launch also carries the d finite-
+        // difference points around the full-step candidate: when the full step is accepted (the common case) the
+        // next gradient is already there.  Same iterates as one-size-at-a-time backtracking, ~3x fewer launches.
+        for (size_t i = 0; i < n; i++) { t[i] = 1.0; todo[i] = active[i]; fn[i] = f[i]; grad_done[i] = 0; }
         xn = x;
-        for (int bt = 0; bt < o.max_backtrack; bt++) {
+        gn = g;
+        int tried = 0;
+        for (int round = 0; tried < o.max_backtrack; round++) {
             rows.clear();
             for (size_t i = 0; i < n; i++) if (todo[i]) rows.push_back(i);
             if (rows.empty()) break;
+            const int nt = std::min(4, o.max_backtrack - tried);
+            const bool spec = (round == 0);
+            const size_t per_row = (size_t)nt + (spec ? d : 0);
             size_t k = 0;
             for (size_t i : rows) {
-                for (size_t j = 0; j < d; j++)
-                    ev.in.p[k * d + j] = std::min(std::max(x[i * d + j] + t[i] * dir[i * d + j], lower[j]), upper[j]);
+                double* base = ev.in.p + k * per_row * d;
+                double tk = t[i];
+                for (int c = 0; c < nt; c++, tk *= 0.5)
+                    for (size_t j = 0; j < d; j++)
+                        base[(size_t)c * d + j] = std::min(std::max(x[i * d + j] + tk * dir[i * d + j], lower[j]), upper[j]);
+                if (spec)
+                    for (size_t j = 0; j < d; j++) {
+                        double* pt = base + ((size_t)nt + j) * d;
+                        std::memcpy(pt, base, d * sizeof(double));
+                        pt[j] += (base[j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+                    }
                 k++;
             }
-            rc = ev.run(k, ftmp.data());
+            rc = ev.run(k * per_row, fbig.data());
             if (rc) return rc;
             k = 0;
             for (size_t i : rows) {
-                if (ftmp[k] <= f[i] + 1e-4 * t[i] * slope[i]) {
-                    std::memcpy(&xn[i * d], ev.in.p + k * d, d * sizeof(double));
-                    fn[i] = ftmp[k];
+                const double* fr = &fbig[k * per_row];
+                const double* base = ev.in.p + k * per_row * d;
+                double tk = t[i];
+                int hit = -1;
+                for (int c = 0; c < nt; c++, tk *= 0.5)
+                    if (fr[c] <= f[i] + 1e-4 * tk * slope[i]) { hit = c; break; }
+                if (hit >= 0) {
+                    std::memcpy(&xn[i * d], base + (size_t)hit * d, d * sizeof(double));
+                    fn[i] = fr[hit];
                     todo[i] = 0;
+                    if (spec && hit == 0) {
+                        for (size_t j = 0; j < d; j++) {
+                            const double h = (base[j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+                            const double fv = fr[(size_t)nt + j];
+                            gn[i * d + j] = (std::fabs(fv) >= BIG) ? 0.0 : (fv - fn[i]) / h;
+                        }
+                        grad_done[i] = 1;
+                    }
                 } else {
-                    t[i] *= 0.5;
+                    for (int c = 0; c < nt; c++) t[i] *= 0.5;
                 }
                 k++;
             }
+            tried += nt;
         }
         rows.clear();
         for (size_t i = 0; i < n; i++) {
             moved[i] = active[i] && !todo[i];
-            if (moved[i]) rows.push_back(i);
+            if (moved[i] && !grad_done[i]) rows.push_back(i);
         }
-        gn = g;
         if (!rows.empty()) {
             rc = grad(rows, xn, fn, gn);
             if (rc) return rc;
