@@ -53,6 +53,7 @@ struct PTParams {
     // series statistics for the starting values
     double y_mean, y_var_sample, y_var_pop, median_dt, tspan;
     int ny;
+    int series_in_smem;  // 1: sdt/sy/se of the log-density calls point into shared memory
     // device buffers
     const double* init;  // d values or nullptr
     double* samples;     // [n_ens][nsamples][d]
@@ -145,7 +146,15 @@ __device__ __noinline__ double logdensity_resident(const PTParams& pp, const dou
     LogLikAcc acc;
     kf.reset(prm, e2_0);
     acc.init();
-    filter_span_any<P, true>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+    if (pp.series_in_smem) {
+        // tell the compiler the address space: LDS with a uniform address instead of generic loads
+        __builtin_assume(__isShared(sdt));
+        __builtin_assume(__isShared(sy));
+        __builtin_assume(__isShared(se));
+        filter_span_any<P, false>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+    } else {
+        filter_span_any<P, true>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+    }
     return acc.value() + prm.logprior;
 }
 
@@ -552,6 +561,7 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
     }
     // series resident in shared memory when it fits (<= 96 KiB keeps at least two blocks per SM)
     mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= PT_SMEM_MAX ? 1 : 0;
+    pp.series_in_smem = mm.resident;
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
     if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;
