@@ -138,6 +138,17 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _reduce_secondary(dist, torch, ms, err):
+    """max-over-ranks time of a secondary measurement; every rank calls this (also after a local failure), so a
+    rank that failed cannot leave the others waiting in a collective."""
+    failed = 0.0 if err is None else 1.0
+    if dist:
+        tt = torch.tensor([ms if err is None else -1.0, failed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, failed = float(tt[0].item()), float(tt[1].item())
+    return ms, failed > 0
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import carma_pack_b200 as C
@@ -276,122 +287,144 @@ def run_ours(args, rank, world, local_rank):
     same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy(), equal_nan=True))
 
     # ---- PT-MCMC secondary metric (BASELINE config 3 shape: 10 temperatures, ny=1000, on-device adapt/exchange)
+    # (secondary measurements are guarded: a failure is reported in their own block, never in place of the line)
     pt = None
     if not args.no_pt:
         from carma_pack_b200 import synth
         n_ens = args.pt_ensembles
-        tp, yp, ep = synth.readme_series(1000, 1000)
-        sp = C.Series(tp, yp, ep, device=dev)
-        ppr = sp.default_prior()
-        o = C.PTOpts()
-        lib.carma_pt_default_opts(ctypes.byref(o))
-        o.nsamples, o.burnin, o.thin, o.ntemps = args.pt_iters // 2, args.pt_iters - args.pt_iters // 2, 1, 10
-        o.seed, o.ensemble_offset = 4096, rank * n_ens
-        iters = o.burnin + o.nsamples
-        ds = torch.empty(n_ens * o.nsamples * d, dtype=torch.float64, device="cuda")
-        dl = torch.empty(n_ens * o.nsamples, dtype=torch.float64, device="cuda")
-        o_w = C.PTOpts.from_buffer_copy(o)
-        o_w.nsamples, o_w.burnin = 1, 1
-        sp.pt_run_dev(C.KIND_CARMA, P, Q, o_w, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)  # warm-up
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        sp.pt_run_dev(C.KIND_CARMA, P, Q, o, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)
-        b.record()
-        torch.cuda.synchronize()
-        pt_ms = a.elapsed_time(b)
-        if dist:
-            tt = torch.tensor([pt_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            pt_ms = float(tt.item())
-        # the launch also draws starting values: (iters + ~1 start eval) evals per chain
-        pt = {"metric": "PT-MCMC ensemble-iterations/s, CARMA(5,3), ny=1000, 10 temperatures, order=reference(pipelined)",
-              "value": world * n_ens * iters / (pt_ms * 1e-3), "unit": "ensemble-iters/s",
-              "implied_evals_per_s": world * n_ens * iters * 10 / (pt_ms * 1e-3),
-              "ensembles_per_gpu": n_ens, "iterations": iters, "ms": pt_ms, "kernel_launches": 1,
-              "includes": "starting-value draws (>= 1 log-density per chain) and the ntemps-1 fill/drain ticks of the "
-                          "pipelined reference step order, all inside the one timed launch",
-              "tflops_algorithmic": world * n_ens * iters * 10 * f_eval(P, 1000) / (pt_ms * 1e-3) / 1e12,
-              "finite_logposts": bool(torch.isfinite(dl).all().item())}
-        sp.close()
+        pt_ms, pt_err, iters, pt_finite, sp = 0.0, None, 0, False, None
+        try:
+            tp, yp, ep = synth.readme_series(1000, 1000)
+            sp = C.Series(tp, yp, ep, device=dev)
+            ppr = sp.default_prior()
+            o = C.PTOpts()
+            lib.carma_pt_default_opts(ctypes.byref(o))
+            o.nsamples, o.burnin, o.thin, o.ntemps = args.pt_iters // 2, args.pt_iters - args.pt_iters // 2, 1, 10
+            o.seed, o.ensemble_offset = 4096, rank * n_ens
+            iters = o.burnin + o.nsamples
+            ds = torch.empty(n_ens * o.nsamples * d, dtype=torch.float64, device="cuda")
+            dl = torch.empty(n_ens * o.nsamples, dtype=torch.float64, device="cuda")
+            o_w = C.PTOpts.from_buffer_copy(o)
+            o_w.nsamples, o_w.burnin = 1, 1
+            sp.pt_run_dev(C.KIND_CARMA, P, Q, o_w, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)  # warm-up
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            sp.pt_run_dev(C.KIND_CARMA, P, Q, o, n_ens, ds.data_ptr(), dl.data_ptr(), ppr, stream=stream)
+            b.record()
+            torch.cuda.synchronize()
+            pt_ms = a.elapsed_time(b)
+            pt_finite = bool(torch.isfinite(dl).all().item())
+            del ds, dl
+        except Exception as ex:  # noqa: BLE001
+            pt_err = "%s: %s" % (type(ex).__name__, ex)
+        finally:
+            if sp is not None:
+                sp.close()
+        pt_ms, pt_failed = _reduce_secondary(dist, torch, pt_ms, pt_err)
+        if pt_failed:
+            pt = {"error": pt_err or "failed on another rank"}
+        else:
+            # the launch also draws starting values: (iters + ~1 start eval) evals per chain
+            pt = {"metric": "PT-MCMC ensemble-iterations/s, CARMA(5,3), ny=1000, 10 temperatures, order=reference(pipelined)",
+                  "value": world * n_ens * iters / (pt_ms * 1e-3), "unit": "ensemble-iters/s",
+                  "implied_evals_per_s": world * n_ens * iters * 10 / (pt_ms * 1e-3),
+                  "ensembles_per_gpu": n_ens, "iterations": iters, "ms": pt_ms, "kernel_launches": 1,
+                  "includes": "starting-value draws (>= 1 log-density per chain) and the ntemps-1 fill/drain ticks of the "
+                              "pipelined reference step order, all inside the one timed launch",
+                  "tflops_algorithmic": world * n_ens * iters * 10 * f_eval(P, 1000) / (pt_ms * 1e-3) / 1e12,
+                  "finite_logposts": pt_finite}
 
     # ---- survey-scale secondary metric (BASELINE config 5): one CARMA(3,1) theta per light curve, ny = 1000
     survey = None
     if not args.no_survey:
         from carma_pack_b200 import synth
         ncv, nyc = args.survey_curves, 1000
-        rng = np.random.default_rng(5000 + rank)
-        # the light curves are drawn from the CARMA(3,1) truth ON the device (carma_multi_series_simulate):
-        # 24 bytes per point never cross PCIe, which is what lets one GPU hold the 10^6-curve survey
-        th_true = synth.carma31_theta(sigmay=1.0, mu=0.0)
-        t_gen = time.perf_counter()
-        ms_ = C.MultiSeries.simulate(ncv, nyc, C.KIND_CARMA, 3, 1, th_true, yerr=0.3, dt_min=0.1, dt_max=1e3,
-                                     seed=5000, curve_offset=rank * ncv, device=dev)
-        t_gen = time.perf_counter() - t_gen
-        th31 = np.tile(th_true, (ncv, 1))
-        th31[:, 3:] += 0.05 * rng.standard_normal((ncv, 4))
-        d_pr = torch.from_numpy(ms_.default_priors().view(np.float64).reshape(ncv, 6)).cuda()
-        d_th = torch.from_numpy(th31).cuda()
-        d_o = torch.empty(ncv, dtype=torch.float64, device="cuda")
-        for _ in range(2):
-            ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
-        torch.cuda.synchronize()
-        reps = 5
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tot = 0.0
-        for _ in range(reps):
-            flush.zero_()
-            a.record()
-            ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
-            b.record()
+        sv_ms, sv_err, t_gen, sv_finite, ms_ = 0.0, None, 0.0, 0.0, None
+        try:
+            rng = np.random.default_rng(5000 + rank)
+            # the light curves are drawn from the CARMA(3,1) truth ON the device (carma_multi_series_simulate):
+            # 24 bytes per point never cross PCIe, which is what lets one GPU hold the 10^6-curve survey
+            th_true = synth.carma31_theta(sigmay=1.0, mu=0.0)
+            t_gen = time.perf_counter()
+            ms_ = C.MultiSeries.simulate(ncv, nyc, C.KIND_CARMA, 3, 1, th_true, yerr=0.3, dt_min=0.1, dt_max=1e3,
+                                         seed=5000, curve_offset=rank * ncv, device=dev)
+            t_gen = time.perf_counter() - t_gen
+            th31 = np.tile(th_true, (ncv, 1))
+            th31[:, 3:] += 0.05 * rng.standard_normal((ncv, 4))
+            d_pr = torch.from_numpy(ms_.default_priors().view(np.float64).reshape(ncv, 6)).cuda()
+            d_th = torch.from_numpy(th31).cuda()
+            d_o = torch.empty(ncv, dtype=torch.float64, device="cuda")
+            for _ in range(2):
+                ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
             torch.cuda.synchronize()
-            tot += a.elapsed_time(b)
-        sv_ms = tot / reps
-        if dist:
-            tt_ = torch.tensor([sv_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-            sv_ms = float(tt_.item())
-        survey = {"metric": "multi light-curve LogDensity, CARMA(3,1), ny=1000, one theta per curve",
-                  "value": world * ncv / (sv_ms * 1e-3), "unit": "curves/s", "curves_per_gpu": ncv, "ms": sv_ms,
-                  "hbm_gbs_algorithmic": ncv * nyc * 24 / (sv_ms * 1e-3) / 1e9,
-                  "tflops_algorithmic": ncv * f_eval(3, nyc) / (sv_ms * 1e-3) / 1e12,
-                  "finite": float(torch.isfinite(d_o).float().mean().item()),
-                  "generate_s": t_gen,
-                  "data": "synthetic, generated in HBM: Cauchy-gap times (generate_test_data.py:17), CARMA(3,1) draws + N(0,0.3^2) noise"}
-        ms_.close()
-        del d_pr, d_th, d_o
+            reps = 5
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a.record()
+                ms_.loglik_dev(C.KIND_CARMA, 3, 1, d_pr.data_ptr(), d_th.data_ptr(), d_o.data_ptr(), 0, stream)
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+            sv_ms = tot / reps
+            sv_finite = float(torch.isfinite(d_o).float().mean().item())
+            del d_pr, d_th, d_o
+        except Exception as ex:  # noqa: BLE001
+            sv_err = "%s: %s" % (type(ex).__name__, ex)
+        finally:
+            if ms_ is not None:
+                ms_.close()
+        sv_ms, sv_failed = _reduce_secondary(dist, torch, sv_ms, sv_err)
+        if sv_failed:
+            survey = {"error": sv_err or "failed on another rank"}
+        else:
+            survey = {"metric": "multi light-curve LogDensity, CARMA(3,1), ny=1000, one theta per curve",
+                      "value": world * ncv / (sv_ms * 1e-3), "unit": "curves/s", "curves_per_gpu": ncv, "ms": sv_ms,
+                      "hbm_gbs_algorithmic": ncv * nyc * 24 / (sv_ms * 1e-3) / 1e9,
+                      "tflops_algorithmic": ncv * f_eval(3, nyc) / (sv_ms * 1e-3) / 1e12,
+                      "finite": sv_finite,
+                      "generate_s": t_gen,
+                      "data": "synthetic, generated in HBM: Cauchy-gap times (generate_test_data.py:17), CARMA(3,1) draws + N(0,0.3^2) noise"}
 
     # ---- single very long series through the associative-scan kernel (BASELINE config 5, ny = 10^6)
     scan = None
     if not args.no_scan and rank == 0:
-        from carma_pack_b200 import synth
-        nl = args.scan_ny
-        rng = np.random.default_rng(77)
-        tl = np.cumsum(rng.uniform(0.5, 1.5, nl))
-        sl = C.Series(tl, rng.standard_normal(nl), np.full(nl, 0.3), device=dev)
-        ar31, _, _ = synth.carma31_truth()
-        th1 = torch.tensor([[1.0, 1.0, 0.0] + list(synth.roots_to_logquad(ar31)) + [np.log(1.0 / 3.0)]], dtype=torch.float64).cuda()
-        o1 = torch.empty(1, dtype=torch.float64, device="cuda")
-        o2 = torch.empty(1, dtype=torch.float64, device="cuda")
-        prl = sl.default_prior()
-        sl.loglik_scan_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o1.data_ptr(), 1, prl, C.IGNORE_BOUNDS, 0, stream)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(5):
+        sl = None
+        try:
+            from carma_pack_b200 import synth
+            nl = args.scan_ny
+            rng = np.random.default_rng(77)
+            tl = np.cumsum(rng.uniform(0.5, 1.5, nl))
+            sl = C.Series(tl, rng.standard_normal(nl), np.full(nl, 0.3), device=dev)
+            ar31, _, _ = synth.carma31_truth()
+            th1 = torch.tensor([[1.0, 1.0, 0.0] + list(synth.roots_to_logquad(ar31)) + [np.log(1.0 / 3.0)]], dtype=torch.float64).cuda()
+            o1 = torch.empty(1, dtype=torch.float64, device="cuda")
+            o2 = torch.empty(1, dtype=torch.float64, device="cuda")
+            prl = sl.default_prior()
             sl.loglik_scan_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o1.data_ptr(), 1, prl, C.IGNORE_BOUNDS, 0, stream)
-        b.record()
-        torch.cuda.synchronize()
-        scan_ms = a.elapsed_time(b) / 5
-        a.record()
-        sl.loglik_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o2.data_ptr(), 1, prl, C.IGNORE_BOUNDS, stream)
-        b.record()
-        torch.cuda.synchronize()
-        seq_ms = a.elapsed_time(b)
-        scan = {"metric": "one CARMA(3,1) LogDensity on a single ny=%d series, associative-scan kernels (5 launches)" % nl,
-                "ms": scan_ms, "points_per_s": nl / (scan_ms * 1e-3), "sequential_one_thread_ms": seq_ms,
-                "rel_diff_vs_sequential": abs(float(o1.item()) - float(o2.item())) / abs(float(o2.item()))}
-        sl.close()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                sl.loglik_scan_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o1.data_ptr(), 1, prl, C.IGNORE_BOUNDS, 0, stream)
+            b.record()
+            torch.cuda.synchronize()
+            scan_ms = a.elapsed_time(b) / 5
+            a.record()
+            sl.loglik_dev(C.KIND_CARMA, 3, 1, th1.data_ptr(), o2.data_ptr(), 1, prl, C.IGNORE_BOUNDS, stream)
+            b.record()
+            torch.cuda.synchronize()
+            seq_ms = a.elapsed_time(b)
+            scan = {"metric": "one CARMA(3,1) LogDensity on a single ny=%d series, associative-scan kernels (5 launches)" % nl,
+                    "ms": scan_ms, "points_per_s": nl / (scan_ms * 1e-3), "sequential_one_thread_ms": seq_ms,
+                    "rel_diff_vs_sequential": abs(float(o1.item()) - float(o2.item())) / abs(float(o2.item()))}
+        except Exception as ex:  # noqa: BLE001
+            scan = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        finally:
+            if sl is not None:
+                sl.close()
 
     clocks = sampler.stop() if sampler else None
 

@@ -326,6 +326,7 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    (void)cudaGetLastError();  // a reported (non-sticky) error must not resurface in a later, unrelated launch check
     return false;
 }
 bool DevBuf::reserve(size_t bytes) {

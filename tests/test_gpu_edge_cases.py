@@ -147,3 +147,18 @@ def test_pt_on_series_too_long_for_shared_memory(C, O):
     ores = O.pt_run(O.KIND_CARP, 2, 0, tl, yl, el, 6, 6, ntemps=3, seed=5, prior=O.default_prior(tl, yl))
     np.testing.assert_allclose(res["samples"][0], ores["samples"], rtol=1e-7, atol=1e-9)
     sl.close()
+
+
+def test_reported_cuda_error_does_not_leak_into_later_calls(C):
+    """An allocation failure is reported once (CarmaError) and leaves the library usable: the stale CUDA error
+    must not resurface in the launch check of a later, unrelated call."""
+    from carma_pack_b200 import synth
+    th = synth.carma31_theta()
+    with pytest.raises(C.CarmaError):
+        C.MultiSeries.simulate(40_000_000, 1000, C.KIND_CARMA, 3, 1, th)   # 960 GB: cudaMalloc fails
+    t, y, e = synth.readme_series(120, 3)
+    s = C.Series(t, y, e)
+    got = s.loglik_scan(C.KIND_CARMA, 3, 1, th[None, :], flags=C.IGNORE_BOUNDS)
+    seq = s.loglik(C.KIND_CARMA, 3, 1, th[None, :], flags=C.IGNORE_BOUNDS)
+    assert np.isfinite(got[0]) and abs(got[0] - seq[0]) <= 1e-9 * abs(seq[0])
+    s.close()
