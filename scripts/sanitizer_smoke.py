@@ -24,4 +24,15 @@ ms = C.MultiSeries(np.concatenate(ts), np.concatenate(ys), np.concatenate(es), o
 thm = np.vstack([synth.prior_draws(1, 3, 1, ts[c], ys[c], rng) for c in range(9)])
 lm = ms.loglik(C.KIND_CARMA, 3, 1, thm)
 rm = ms.pt_run(C.KIND_CARMA, 3, 1, 3, 3, ntemps=4, n_ensembles=2, seed=4)
-print("ok", np.isfinite(lp).mean(), lp2[:2], m[:2], qv, r["logposts"].shape, r1["logposts"].shape, lm[:3], rm["logposts"].shape)
+# all orders through K1 (shared-memory LU scratch of every size, incl. the > 48 KiB opt-in at P = 7)
+for p_, q_ in ((1, 0), (2, 1), (3, 0), (4, 2), (6, 3), (7, 5)):
+    kind_ = C.KIND_CAR1 if p_ == 1 else (C.KIND_CARMA if q_ else C.KIND_CARP)
+    thp = np.tile(np.array([1.0, 1.0, 0.0, np.log(0.1)]), (70, 1)) if p_ == 1 else synth.prior_draws(70, p_, q_, t, y, rng)
+    s.loglik(kind_, p_, q_, thp, prior=pr)
+sim = C.MultiSeries.simulate(130, 40, C.KIND_CARMA, 3, 1, synth.carma31_theta(), seed=3)
+ls = sim.loglik(C.KIND_CARMA, 3, 1, np.tile(synth.carma31_theta(), (130, 1)))
+tc = sim.curve(129)
+lo_, hi_ = np.full(7, -10.0), np.full(7, 10.0)
+xm, fm, nit, nfev = s.mle_batch(C.KIND_CARMA, 3, 1, synth.prior_draws(6, 3, 1, t, y, rng), lo_, hi_, prior=pr,
+                                flags=C.IGNORE_BOUNDS, maxiter=3)
+print("ok", np.isfinite(lp).mean(), lp2[:2], m[:2], qv, r["logposts"].shape, r1["logposts"].shape, lm[:3], rm["logposts"].shape, ls[:2], tc[0][:2], fm[:2], nit, nfev)
