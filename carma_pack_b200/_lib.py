@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "carma_log_prior", "carma_loglik_scan_dev", "carma_loglik_scan",
     "carma_multi_series_create", "carma_multi_series_destroy", "carma_multi_series_default_priors",
     "carma_multi_series_simulate", "carma_multi_series_get_curve",
-    "carma_mle_default_opts", "carma_mle_batch",
+    "carma_mle_default_opts", "carma_mle_batch", "carma_lbfgs_batch",
     "carma_multi_loglik_dev", "carma_multi_loglik",
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
@@ -67,6 +67,7 @@ TRACE_DTYPE = np.dtype([("lp_prop", "f8"), ("lp_cur", "f8"), ("alpha", "f8"), ("
 _dp = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p
 _sz = ctypes.c_size_t
+OBJECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _dp, _sz, _sz, _dp, _vp)
 
 
 def _load():
@@ -102,6 +103,8 @@ def _load():
     L.carma_multi_series_get_curve.argtypes = [_vp, _sz, _dp, _dp, _dp, _sz, ctypes.POINTER(_sz)]
     L.carma_mle_default_opts.argtypes = [ctypes.POINTER(MLEOpts)]
     L.carma_mle_default_opts.restype = None
+    L.carma_lbfgs_batch.argtypes = [OBJECTIVE_FN, _vp, _sz, _sz, _dp, _dp, _dp, ctypes.POINTER(MLEOpts), _dp, _dp,
+                                    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)]
     L.carma_mle_batch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.c_uint, _sz, _dp, _dp, _dp,
                                   ctypes.POINTER(MLEOpts), _dp, _dp, ctypes.POINTER(ctypes.c_int),
                                   ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
@@ -417,6 +420,32 @@ class MultiSeries:
     def loglik_dev(self, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags=0, stream=0):
         check(lib.carma_multi_loglik_dev(self.handle, kind, p, q, d_priors_ptr, d_theta_ptr, d_out_ptr, flags, stream),
               "carma_multi_loglik_dev")
+
+
+def lbfgs_batch(fun_batch, x0, lower, upper, maxiter=200, history=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
+    """The native optimiser core (carma_lbfgs_batch) on a Python objective: fun_batch maps an (n, d) array to n
+    values.  Host code only; this is the loop Series.mle_batch runs with the GPU log-density as objective."""
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n, d = x0.shape
+    lo, hi = _c(np.broadcast_to(lower, (d,))), _c(np.broadcast_to(upper, (d,)))
+
+    def trampoline(theta, npts, dim, fout, _user):
+        try:
+            th = np.ctypeslib.as_array(theta, shape=(npts, dim))
+            np.ctypeslib.as_array(fout, shape=(npts,))[:] = np.asarray(fun_batch(th.copy()), dtype=np.float64)
+            return 0
+        except Exception:  # noqa: BLE001
+            return 1
+
+    cb = OBJECTIVE_FN(trampoline)
+    o = MLEOpts()
+    lib.carma_mle_default_opts(ctypes.byref(o))
+    o.maxiter, o.history, o.gtol, o.ftol, o.fd_eps = int(maxiter), int(history), gtol, ftol, fd_eps
+    x, f = np.empty((n, d)), np.empty(n)
+    nit, nfev = ctypes.c_int(0), ctypes.c_longlong(0)
+    check(lib.carma_lbfgs_batch(cb, None, d, n, _ptr(x0), _ptr(lo), _ptr(hi), ctypes.byref(o), _ptr(x), _ptr(f),
+                                ctypes.byref(nit), ctypes.byref(nfev)), "carma_lbfgs_batch")
+    return x, f, nit.value, nfev.value
 
 
 def log_prior(kind, p, theta, prior):

@@ -53,18 +53,24 @@ struct PinnedBuf {
     ~PinnedBuf() { if (p) cudaFreeHost(p); }
 };
 
-struct Evaluator {
+// what the optimiser minimises: a batch of points staged in `in` -> their function values
+struct Objective {
+    double* in = nullptr;   // staging buffer for the points of the next run(): capacity n (d + 4) d doubles
+    long long nfev = 0;
+    virtual int run(size_t n, double* f) = 0;  // f[k] for the first n staged points; non-finite -> BIG
+    virtual ~Objective() {}
+};
+
+// -LogDensity(theta) through K1 (pinned buffers, the series' stream slot)
+struct GpuObjective : Objective {
     carma_series_t s;
     int kind, p, q, slot;
     const carma_prior_t* prior;
     unsigned flags;
-    size_t d;
-    PinnedBuf in, out;
-    long long nfev = 0;
-    // f[k] = -LogDensity(theta_k) for k < n; non-finite -> BIG.  theta rows are already in in.p.
-    int run(size_t n, double* f) {
+    PinnedBuf inbuf, out;
+    int run(size_t n, double* f) override {
         if (n == 0) return CARMA_OK;
-        int rc = carma_loglik_batch_async(s, kind, p, q, prior, n, in.p, out.p, flags, slot);
+        int rc = carma_loglik_batch_async(s, kind, p, q, prior, n, inbuf.p, out.p, flags, slot);
         if (rc) return rc;
         rc = carma_loglik_batch_wait(s, slot);
         if (rc) return rc;
@@ -77,7 +83,36 @@ struct Evaluator {
     }
 };
 
+// a caller-supplied objective (carma_lbfgs_batch): used by the CPU tests of the optimiser core
+struct CallbackObjective : Objective {
+    carma_objective_fn fn;
+    void* user;
+    size_t d;
+    std::vector<double> buf;
+    int run(size_t n, double* f) override {
+        if (n == 0) return CARMA_OK;
+        int rc = fn(in, n, d, f, user);
+        if (rc) { set_error("carma_lbfgs_batch: the objective callback reported an error"); return CARMA_ERR_ARG; }
+        for (size_t k = 0; k < n; k++)
+            if (!std::isfinite(f[k])) f[k] = BIG;
+        nfev += (long long)n;
+        return CARMA_OK;
+    }
+};
+
+int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double* lower, const double* upper,
+               const carma_mle_opts_t& o, double* x_out, double* f_out, int* nit_out, long long* nfev_out);
+
 }  // namespace
+
+static int check_opts(const carma_mle_opts_t* opts, carma_mle_opts_t& o, const char* who) {
+    if (opts) o = *opts; else carma_mle_default_opts(&o);
+    if (o.maxiter < 0 || o.history < 1 || o.history > 64 || o.max_backtrack < 1 || !(o.fd_eps > 0)) {
+        set_error(std::string(who) + ": invalid options");
+        return CARMA_ERR_ARG;
+    }
+    return CARMA_OK;
+}
 
 extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
                                size_t nstart, const double* x0, const double* lower, const double* upper,
@@ -93,21 +128,42 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
         return CARMA_ERR_ARG;
     }
     carma_mle_opts_t o;
-    if (opts) o = *opts; else carma_mle_default_opts(&o);
-    if (o.maxiter < 0 || o.history < 1 || o.history > 64 || o.max_backtrack < 1 || !(o.fd_eps > 0)) {
-        set_error("carma_mle_batch: invalid options");
-        return CARMA_ERR_ARG;
-    }
+    int rc = check_opts(opts, o, "carma_mle_batch");
+    if (rc) return rc;
     if (nit_out) *nit_out = 0;
     if (nfev_out) *nfev_out = 0;
     if (nstart == 0) return CARMA_OK;
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
-
     const size_t n = nstart, d = (size_t)model_dim(kind, p, q);
-    const int m = o.history;
-    Evaluator ev{s, kind, p, q, slot, prior, flags, d};
-    if (!ev.in.reserve(n * (d + 4) * d) || !ev.out.reserve(n * (d + 4))) { set_error("carma_mle_batch: pinned allocation failed"); return CARMA_ERR_ALLOC; }
+    GpuObjective ev;
+    ev.s = s; ev.kind = kind; ev.p = p; ev.q = q; ev.slot = slot; ev.prior = prior; ev.flags = flags;
+    if (!ev.inbuf.reserve(n * (d + 4) * d) || !ev.out.reserve(n * (d + 4))) { set_error("carma_mle_batch: pinned allocation failed"); return CARMA_ERR_ALLOC; }
+    ev.in = ev.inbuf.p;
+    return lbfgs_core(ev, n, d, x0, lower, upper, o, x_out, f_out, nit_out, nfev_out);
+}
 
+extern "C" int carma_lbfgs_batch(carma_objective_fn fn, void* user, size_t d, size_t nstart, const double* x0,
+                                 const double* lower, const double* upper, const carma_mle_opts_t* opts, double* x_out,
+                                 double* f_out, int* nit_out, long long* nfev_out) {
+    if (!fn || !x0 || !lower || !upper || !x_out || !f_out || d == 0) { set_error("carma_lbfgs_batch: bad argument"); return CARMA_ERR_ARG; }
+    carma_mle_opts_t o;
+    int rc = check_opts(opts, o, "carma_lbfgs_batch");
+    if (rc) return rc;
+    if (nit_out) *nit_out = 0;
+    if (nfev_out) *nfev_out = 0;
+    if (nstart == 0) return CARMA_OK;
+    CallbackObjective ev;
+    ev.fn = fn; ev.user = user; ev.d = d;
+    ev.buf.resize(nstart * (d + 4) * d);
+    ev.in = ev.buf.data();
+    return lbfgs_core(ev, nstart, d, x0, lower, upper, o, x_out, f_out, nit_out, nfev_out);
+}
+
+namespace {
+
+int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double* lower, const double* upper,
+               const carma_mle_opts_t& o, double* x_out, double* f_out, int* nit_out, long long* nfev_out) {
+    const int m = o.history;
     std::vector<double> x(n * d), f(n), g(n * d), xn(n * d), fn(n), gn(n * d), pg(n * d), qv(n * d), dir(n * d), slope(n), t(n);
     std::vector<double> S((size_t)m * n * d), Y((size_t)m * n * d), alpha((size_t)m * n), rho((size_t)m * n), ftmp(n * d);
     std::vector<char> active(n), todo(n), moved(n), blocked(n * d), grad_done(n);
@@ -125,9 +181,9 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
         size_t k = 0;
         for (size_t i : rr)
             for (size_t j = 0; j < d; j++, k++) {
-                std::memcpy(ev.in.p + k * d, &z[i * d], d * sizeof(double));
+                std::memcpy(ev.in + k * d, &z[i * d], d * sizeof(double));
                 double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
-                ev.in.p[k * d + j] += h;
+                ev.in[k * d + j] += h;
             }
         int rc = ev.run(k, ftmp.data());
         if (rc) return rc;
@@ -140,7 +196,7 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
         return CARMA_OK;
     };
 
-    std::memcpy(ev.in.p, x.data(), n * d * sizeof(double));
+    std::memcpy(ev.in, x.data(), n * d * sizeof(double));
     int rc = ev.run(n, f.data());
     if (rc) return rc;
     rows.resize(n);
@@ -232,7 +288,7 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
             const size_t per_row = (size_t)nt + (spec ? d : 0);
             size_t k = 0;
             for (size_t i : rows) {
-                double* base = ev.in.p + k * per_row * d;
+                double* base = ev.in + k * per_row * d;
                 double tk = t[i];
                 for (int c = 0; c < nt; c++, tk *= 0.5)
                     for (size_t j = 0; j < d; j++)
@@ -250,7 +306,7 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
             k = 0;
             for (size_t i : rows) {
                 const double* fr = &fbig[k * per_row];
-                const double* base = ev.in.p + k * per_row * d;
+                const double* base = ev.in + k * per_row * d;
                 double tk = t[i];
                 int hit = -1;
                 for (int c = 0; c < nt; c++, tk *= 0.5)
@@ -327,3 +383,5 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
     if (nfev_out) *nfev_out = ev.nfev;
     return CARMA_OK;
 }
+
+}  // namespace

@@ -136,6 +136,13 @@ typedef struct carma_mle_opts {
     double fd_eps;      /* forward-difference step, 1e-8 (scipy approx_grad epsilon) */
 } carma_mle_opts_t;
 void carma_mle_default_opts(carma_mle_opts_t* o);
+/* The optimiser core on a caller-supplied objective (host code only, no GPU involved): fn evaluates n points
+ * (theta: n x d, row-major) into f and returns 0 on success; non-finite values count as +infinity.  This is the
+ * loop carma_mle_batch runs with -LogDensity as the objective; exported so that it can be exercised on its own. */
+typedef int (*carma_objective_fn)(const double* theta, size_t n, size_t d, double* f, void* user);
+int carma_lbfgs_batch(carma_objective_fn fn, void* user, size_t d, size_t nstart, const double* x0,
+                      const double* lower, const double* upper, const carma_mle_opts_t* opts, double* x_out,
+                      double* f_out, int* nit_out, long long* nfev_out);
 int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
                     size_t nstart, const double* x0, const double* lower, const double* upper,
                     const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out, long long* nfev_out,
