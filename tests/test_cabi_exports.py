@@ -39,6 +39,12 @@ def test_struct_layouts_match_header():
     # defaults of RunCarmaSampler: carmcmc.cpp:92, 139, 141; steps.cpp:29
     assert (o.tmax, o.dof, o.target_rate) == (100.0, 8, 0.25)
     assert abs(o.gamma - 2.0 / 3.0) < 1e-16 and o.ntemps == 10 and o.thin == 1
+    assert ctypes.sizeof(C._lib.MLEOpts) == 4 * 4 + 3 * 8
+    m = C._lib.MLEOpts()
+    C._lib.lib.carma_mle_default_opts(ctypes.byref(m))
+    # scipy L-BFGS-B defaults used by the reference's fits (minimize(..., method="L-BFGS-B") at carma_pack.py:250): pgtol 1e-5, factr*eps 2.2e-9, eps 1e-8
+    assert (m.maxiter, m.history, m.max_backtrack) == (200, 8, 25)
+    assert (m.gtol, m.ftol, m.fd_eps) == (1e-5, 2.2e-9, 1e-8)
 
 
 def test_argument_validation_without_gpu():
