@@ -84,3 +84,71 @@ def test_world_size_2_gloo_gather():
     assert np.all(np.isfinite(best0[:, 0]))              # every model was fitted by somebody
     g = res[0][2]
     assert g.shape == (2, 2) and g[:, 1].sum() == 50 and list(g[:, 0]) == [0.0, 1.0]
+
+
+# ---- CarmaModel.choose_order(dist=...) end to end on CPU: the sharding and gather logic with a stand-in fit
+class _FakeSeries:
+    def __init__(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
+
+
+def _fake_get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0, series=None, optimizer="native"):
+    """Deterministic stand-in for a fit: the value of trial j of model (p,q) depends only on (p, q, j), so the
+    best over any partition of the trials must equal the best over all of them."""
+    from scipy.optimize import OptimizeResult
+    d = 4 if p == 1 else 3 + p + q
+    vals = [200.0 + 3.0 * abs(p - 3) + 1.5 * q + ((7 * (trial_offset + j) + 3 * p + q) % 11) * 0.1 for j in range(ntrials)]
+    j = int(np.argmin(vals))
+    return OptimizeResult(x=np.full(d, float(trial_offset + j)), fun=float(vals[j]), success=True)
+
+
+def _choose_order_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import carma_pack_b200.carma_pack as cp
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cp.Series = _FakeSeries
+        cp.CarmaModel.get_mle = _fake_get_mle
+        t = np.arange(120.0)
+        model = cp.CarmaModel(t, np.sin(t), np.full(t.size, 0.1))
+        mle, pqlist, aicc = model.choose_order(4, ntrials=10, seed=1, verbose=False, dist=dist)
+        q.put((rank, list(pqlist), list(aicc), float(mle.fun), np.asarray(mle.x).tolist(), (model.p, model.q)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_choose_order_sharded_over_two_ranks_equals_single_process():
+    import torch.multiprocessing as mp
+    import carma_pack_b200.carma_pack as cp
+    # single process, same stand-in fit
+    saved = (cp.Series, cp.CarmaModel.get_mle)
+    try:
+        cp.Series = _FakeSeries
+        cp.CarmaModel.get_mle = _fake_get_mle
+        t = np.arange(120.0)
+        model = cp.CarmaModel(t, np.sin(t), np.full(t.size, 0.1))
+        mle1, pq1, aicc1 = model.choose_order(4, ntrials=10, seed=1, verbose=False)
+        best1 = (model.p, model.q)
+    finally:
+        cp.Series, cp.CarmaModel.get_mle = saved
+    assert len(pq1) == 10   # p = 1..4, q < p
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_choose_order_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r[1] == [tuple(x) for x in pq1] or r[1] == pq1
+        np.testing.assert_allclose(r[2], aicc1, rtol=0, atol=1e-12)   # same AICc table on every rank
+        assert abs(r[3] - mle1.fun) < 1e-12 and r[5] == best1
+        assert r[4] == np.asarray(mle1.x).tolist()                     # and the same theta-hat (from the best trial)
