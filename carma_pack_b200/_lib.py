@@ -124,7 +124,7 @@ def _load():
                                      _vp, _vp, _vp, _vp]
     L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
     L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
-    L.carma_fastmath_dev.argtypes = [_dp, _sz, _dp, _dp, _dp, _dp]
+    L.carma_fastmath_dev.argtypes = [_dp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]
     L.carma_tdist_dev.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _dp]
     return L
 
@@ -473,8 +473,10 @@ def tdist_dev(seed, chain, it, j, dof=8):
     return out.value
 
 
-def fastmath_dev(x):
-    x = _c(x)
-    e, s, c, r = (np.empty(x.size) for _ in range(4))
-    check(lib.carma_fastmath_dev(_ptr(x), x.size, _ptr(e), _ptr(s), _ptr(c), _ptr(r)), "carma_fastmath_dev")
-    return e, s, c, r
+def fastmath_dev(rate, dt):
+    """The time loop's transcendentals (csrc/fast_math.cuh) on arrays: rate in table steps per unit time.
+    Returns exp(rate dt ln2/32), sin and cos(rate dt pi/64), (1-rho)/2 and (1+rho)/2 with rho = the exponential, 1/rate."""
+    rate, dt = _c(rate), _c(dt)
+    outs = [np.empty(rate.size) for _ in range(6)]
+    check(lib.carma_fastmath_dev(_ptr(rate), _ptr(dt), rate.size, *[_ptr(o) for o in outs]), "carma_fastmath_dev")
+    return tuple(outs)

@@ -41,6 +41,8 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
     fun_batch maps an (n, d) array to n function values (non-finite values are treated as +inf).
     Projected L-BFGS with forward-difference gradients and Armijo backtracking; all rows advance in
     lock-step so that each iteration costs a few batched evaluations (n*(d+1) rows for the gradient).
+    The rows share launches, nothing else: every row keeps its own (s, y) history, so its iterates do not
+    depend on which other rows are in the batch.
     """
     x = np.clip(np.array(x0, dtype=float), lower, upper)
     n, d = x.shape
@@ -50,23 +52,42 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
         v = np.asarray(fun_batch(z), dtype=float)
         return np.where(np.isfinite(v), v, big)
 
+    nfev = 0
+
     def grad(z, fz):
-        # forward differences, stepping inward at the upper bound (scipy approx_fprime epsilon = 1e-8)
+        # forward differences, stepping inward at the upper bound (scipy approx_fprime epsilon = 1e-8); a component
+        # whose perturbed point has no finite value is differenced the other way before it is given up
+        nonlocal nfev
         h = np.full((n, d), fd_eps)
         h = np.where(z + h > upper, -h, h)
         zz = np.repeat(z[:, None, :], d, axis=1)
         idx = np.arange(d)
         zz[:, idx, idx] += h
         fv = f_safe(zz.reshape(n * d, d)).reshape(n, d)
-        g = (fv - fz[:, None]) / h
-        return np.where(np.abs(fv) >= big, 0.0, g)
+        nfev += n * d
+        g = np.where(np.abs(fv) >= big, 0.0, (fv - fz[:, None]) / h)
+        bi, bj = np.nonzero(np.abs(fv) >= big)
+        if bi.size:
+            hb = -h[bi, bj]
+            ok = (z[bi, bj] + hb >= np.broadcast_to(lower, (n, d))[bi, bj]) & (z[bi, bj] + hb <= np.broadcast_to(upper, (n, d))[bi, bj])
+            pts = z[bi].copy()
+            pts[np.arange(bi.size), bj] += np.where(ok, hb, 0.0)
+            fb = f_safe(pts)
+            nfev += bi.size
+            good = ok & (np.abs(fb) < big)
+            g[bi[good], bj[good]] = (fb[good] - fz[bi[good]]) / hb[good]
+        return g
 
     f = f_safe(x)
+    nfev += n
     g = grad(x, f)
-    S, Y = [], []
+    # per-row history, oldest pair first: row i holds nh[i] pairs in S[:nh[i], i] (unused entries are zero)
+    S = np.zeros((m, n, d))
+    Y = np.zeros((m, n, d))
+    nh = np.zeros(n, dtype=int)
     active = f < big
-    nfev = n * (d + 1)
     nit = 0
+    rows = np.arange(n)
     for nit in range(1, maxiter + 1):
         # projected gradient: zero the components pushing against an active bound
         at_lo = (x <= lower) & (g > 0)
@@ -76,22 +97,23 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
         active &= ~conv
         if not active.any():
             break
-        # two-loop recursion, vectorised over rows
+        # two-loop recursion, vectorised over rows; rows with fewer than h+1 pairs skip level h
         qv = pg.copy()
-        alphas = []
-        for s, yv in zip(reversed(S), reversed(Y)):
-            rho = 1.0 / np.maximum(np.sum(s * yv, axis=1), 1e-300)
-            a = rho * np.sum(s * qv, axis=1)
-            qv -= a[:, None] * yv
-            alphas.append((a, rho))
-        if S:
-            gam = np.sum(S[-1] * Y[-1], axis=1) / np.maximum(np.sum(Y[-1] * Y[-1], axis=1), 1e-300)
-            qv *= np.clip(gam, 1e-8, 1e8)[:, None]
-        else:
-            qv *= (1.0 / np.maximum(np.linalg.norm(pg, axis=1), 1.0))[:, None]
-        for (a, rho), s, yv in zip(reversed(alphas), S, Y):
-            b = rho * np.sum(yv * qv, axis=1)
-            qv += (a - b)[:, None] * s
+        alphas = [None] * m
+        for h in range(m - 1, -1, -1):
+            valid = h < nh
+            rho = np.where(valid, 1.0 / np.maximum(np.sum(S[h] * Y[h], axis=1), 1e-300), 0.0)
+            a = rho * np.sum(S[h] * qv, axis=1)
+            qv -= a[:, None] * Y[h]
+            alphas[h] = (a, rho)
+        last = np.maximum(nh - 1, 0)
+        sl, yl = S[last, rows], Y[last, rows]
+        gam = np.clip(np.sum(sl * yl, axis=1) / np.maximum(np.sum(yl * yl, axis=1), 1e-300), 1e-8, 1e8)
+        qv *= np.where(nh > 0, gam, 1.0 / np.maximum(np.linalg.norm(pg, axis=1), 1.0))[:, None]
+        for h in range(m):
+            a, rho = alphas[h]
+            b = rho * np.sum(Y[h] * qv, axis=1)
+            qv += (a - b)[:, None] * S[h]
         direction = -np.where(at_lo | at_hi, 0.0, qv)
         slope = np.sum(direction * pg, axis=1)
         bad = ~(slope < 0)
@@ -116,17 +138,19 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
         gn = g.copy()
         if moved.any():
             gnew = grad(xn, fn)
-            nfev += n * d
             gn[moved] = gnew[moved]
-        s = np.where(moved[:, None], xn - x, 0.0)
-        yv = np.where(moved[:, None], gn - g, 0.0)
-        curv = np.sum(s * yv, axis=1) > 1e-12
-        if curv.any():
-            S.append(np.where(curv[:, None], s, 0.0))
-            Y.append(np.where(curv[:, None], yv, 0.0))
-            if len(S) > m:
-                S.pop(0)
-                Y.pop(0)
+        s = xn - x
+        yv = gn - g
+        curv = moved & (np.sum(s * yv, axis=1) > 1e-12)
+        full = curv & (nh == m)
+        if full.any():   # drop the oldest pair of the rows whose ring is full
+            S[:-1, full] = S[1:, full]
+            Y[:-1, full] = Y[1:, full]
+            nh[full] -= 1
+        ci = np.nonzero(curv)[0]
+        S[nh[ci], ci] = s[ci]
+        Y[nh[ci], ci] = yv[ci]
+        nh[ci] += 1
         x, f, g = xn, fn, gn
         active &= ~todo   # line search failed: stop that row
         active &= ~small

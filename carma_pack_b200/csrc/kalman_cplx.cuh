@@ -20,6 +20,7 @@ struct SeriesView {
     const double* e2n;  // yerr[i+1]^2, e2n[ny-1] = 0
     const double* t;    // t[i]
     double e2_0;        // yerr[0]^2
+    double dt_max;      // longest gap (rate clamp of transform_theta)
     int ny;
     int nyp;            // padded length (even) of dt / y / e2n
 };

@@ -12,10 +12,16 @@
 // What is different from a transliteration (all exact algebraic identities):
 //   * the state is the independent real half z of the rotated complex state (theta_transform.cuh);
 //     the Hadamard product (rho rho^H) o . becomes the block-diagonal congruence Phi . Phi^T with 2x2
-//     blocks  e^{a dt} [[cos, -sin],[sin, cos]]  (conjugate pair) or diag(e^{r1 dt}, e^{r2 dt}) (real pair);
+//     blocks  e^{a dt} [[cos, -sin],[sin, cos]]  (conjugate pair) or  e^{a dt} [[ch, sh],[sh, ch]]  (two real
+//     roots, in the sum/difference basis): every block is [[A, sB],[B, A]] with s = -1 / +1;
 //   * D = P - V is stored instead of P, so V never enters the time loop: g = P b^H = D c + h,
 //     var = c.g + yerr^2, and the predict step is D <- Phi D Phi^T (no subtract/add of V);
-//   * g is computed once per step and reused for the gain, the state update and the variance.
+//   * g is computed once per step and reused for the gain, the state update and the variance;
+//   * the observation row c is (1,0,1,0,...[,1]) for every kind of slot, so g, var and mean are plain sums.
+// The time loop is dispatch bound on sm_100a (fast_math.cuh): it is written to minimise the number of
+// instructions of ANY kind -- one basic block per step, loop constants from the constant bank, shared-memory
+// operands addressed off one register, the sum of log(var) kept as a mantissa product plus an integer exponent
+// sum without any per-step range branch (a sticky flag sends the rare out-of-range case to an exact slow path).
 #pragma once
 #include "fast_math.cuh"
 #include "theta_transform.cuh"
@@ -35,7 +41,7 @@ struct KalmanReal {
 
     static __host__ __device__ constexpr int idx(int i, int j) { return i * P - (i * (i - 1)) / 2 + (j - i); }
 
-    __device__ __forceinline__ void reset(const RealParams<P>& prm, double e2_0) {
+    CARMA_HD void reset(const RealParams<P>& prm, double e2_0) {
 #pragma unroll
         for (int i = 0; i < NT; i++) D[i] = 0.0;
 #pragma unroll
@@ -46,17 +52,16 @@ struct KalmanReal {
 
     // One Update(): condition on the residual `innov` (= y_i - mu - mean_i) observed with predictive
     // variance `var`, move forward by dt, and form mean/var for the next point (measurement variance e2n).
-    // ALLC = true: every 2x2 slot is a conjugate pair (compile-time straight-line code, the common case);
-    // ALLC = false: per-slot run-time selection between conjugate pair and real pair.
+    // ALLC = true: every 2x2 slot is a conjugate pair (compile time; the per-lane selections vanish);
+    // ALLC = false: conjugate and real pairs mixed per lane -- same instruction sequence, operands selected.
     template <bool ALLC>
-    __device__ __forceinline__ void advance(const RealParams<P>& prm, double innov, double inv_var, double dt,
-                                            double e2n) {
+    CARMA_HD void advance(const RealParams<P>& prm, const MathTab& tb, double innov, double inv_var, double dt, double e2n) {
         measurement_update(innov, inv_var);
-        predict_observe<ALLC>(prm, dt, e2n);
+        predict_observe<ALLC>(prm, tb, dt, e2n);
     }
 
     // z += g innov/var ;  D -= g g^T / var   (kfilter.cpp:191-197)
-    __device__ __forceinline__ void measurement_update(double innov, double inv_var) {
+    CARMA_HD void measurement_update(double innov, double inv_var) {
         const double w = innov * inv_var;
         double gi[P];
 #pragma unroll
@@ -70,43 +75,37 @@ struct KalmanReal {
             for (int j = i; j < P; j++) D[idx(i, j)] = fma(-gi[i], g[j], D[idx(i, j)]);
     }
 
-    // transition by dt and predicted observation of the next point (kfilter.cpp:200-210)
+    // the transition blocks [[A, sB],[B, A]] of all slots and the factor of the odd root
     template <bool ALLC>
-    __device__ __forceinline__ void predict_observe(const RealParams<P>& prm, double dt, double e2n) {
-        // ---- transition blocks Phi_s
-        double f00[NS > 0 ? NS : 1], f01[NS > 0 ? NS : 1], f10[NS > 0 ? NS : 1], f11[NS > 0 ? NS : 1];
+    static CARMA_HD void transition(const RealParams<P>& prm, const MathTab& tb, double dt, double* fa, double* fb,
+                                    double* fsb, double* fo) {
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            // the decay factor of the first root is common to both slot types
-            double e = exp_fast(prm.lam[2 * s] * dt);
-            double sn, cs;
-            sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
-            if (ALLC) {
-                f00[s] = e * cs; f01[s] = -(e * sn); f10[s] = e * sn; f11[s] = e * cs;
-            } else {
-                // generic loop: BOTH candidates are evaluated for every lane (lam[2s+1] <= 0 in either
-                // reading, so the extra exp is harmless) and selected per lane -- straight-line code.  A
-                // per-lane branch here costs more than the 12 extra FP64 instructions: mixed warps would
-                // run both sides anyway and the split basic blocks stop ptxas from interleaving the chains
-                // (measured: PT-MCMC config 3, 159 -> 140 ms).
-                const bool is_c = (prm.cmask >> s) & 1u;
-                const double e2 = exp_fast(prm.lam[2 * s + 1] * dt);
-                const double ec = e * cs, es = e * sn;
-                f00[s] = is_c ? ec : e;
-                f01[s] = is_c ? -es : 0.0;
-                f10[s] = is_c ? es : 0.0;
-                f11[s] = is_c ? ec : e2;
-            }
+            const bool is_c = ALLC || ((prm.cmask >> s) & 1u);
+            const double e = exp_scaled(prm.le[s], dt, tb);
+            double s2, c2;
+            rot_scaled<ALLC>(prm.ls[s], dt, is_c, tb, &s2, &c2);
+            fa[s] = e * c2;
+            fb[s] = e * s2;
+            if (ALLC) fsb[s] = -fb[s];
+            else fsb[s] = is_c ? -fb[s] : fb[s];
         }
-        double fo = 1.0;
-        if (ODD) fo = exp_fast(prm.lam[P - 1] * dt);
+        *fo = 1.0;
+        if (ODD) *fo = exp_scaled(prm.le[NS], dt, tb);
+    }
+
+    // transition by dt and predicted observation of the next point (kfilter.cpp:200-210)
+    template <bool ALLC>
+    CARMA_HD void predict_observe(const RealParams<P>& prm, const MathTab& tb, double dt, double e2n) {
+        double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
+        transition<ALLC>(prm, tb, dt, fa, fb, fsb, &fo);
 
         // ---- predict state
 #pragma unroll
         for (int s = 0; s < NS; s++) {
-            double u = z[2 * s], v = z[2 * s + 1];
-            z[2 * s] = fma(f00[s], u, f01[s] * v);
-            z[2 * s + 1] = fma(f10[s], u, f11[s] * v);
+            const double u = z[2 * s], v = z[2 * s + 1];
+            z[2 * s] = fma(fa[s], u, fsb[s] * v);
+            z[2 * s + 1] = fma(fb[s], u, fa[s] * v);
         }
         if (ODD) z[P - 1] *= fo;
 
@@ -114,149 +113,191 @@ struct KalmanReal {
 #pragma unroll
         for (int a = 0; a < NS; a++) {
             const int i = 2 * a;
+            const double A = fa[a], B = fb[a], SB = fsb[a];
             {   // diagonal block (symmetric 2x2)
-                double d00 = D[idx(i, i)], d01 = D[idx(i, i + 1)], d11 = D[idx(i + 1, i + 1)];
-                double m00 = fma(f00[a], d00, f01[a] * d01), m01 = fma(f00[a], d01, f01[a] * d11);
-                double m10 = fma(f10[a], d00, f11[a] * d01), m11 = fma(f10[a], d01, f11[a] * d11);
-                D[idx(i, i)] = fma(m00, f00[a], m01 * f01[a]);
-                D[idx(i, i + 1)] = fma(m00, f10[a], m01 * f11[a]);
-                D[idx(i + 1, i + 1)] = fma(m10, f10[a], m11 * f11[a]);
+                const double d00 = D[idx(i, i)], d01 = D[idx(i, i + 1)], d11 = D[idx(i + 1, i + 1)];
+                const double m00 = fma(A, d00, SB * d01), m01 = fma(A, d01, SB * d11);
+                const double m10 = fma(B, d00, A * d01), m11 = fma(B, d01, A * d11);
+                D[idx(i, i)] = fma(m00, A, m01 * SB);
+                D[idx(i, i + 1)] = fma(m00, B, m01 * A);
+                D[idx(i + 1, i + 1)] = fma(m10, B, m11 * A);
             }
 #pragma unroll
             for (int b = a + 1; b < NS; b++) {  // off-diagonal 2x2 block
                 const int j = 2 * b;
-                double d00 = D[idx(i, j)], d01 = D[idx(i, j + 1)], d10 = D[idx(i + 1, j)], d11 = D[idx(i + 1, j + 1)];
-                double m00 = fma(f00[a], d00, f01[a] * d10), m01 = fma(f00[a], d01, f01[a] * d11);
-                double m10 = fma(f10[a], d00, f11[a] * d10), m11 = fma(f10[a], d01, f11[a] * d11);
-                D[idx(i, j)] = fma(m00, f00[b], m01 * f01[b]);
-                D[idx(i, j + 1)] = fma(m00, f10[b], m01 * f11[b]);
-                D[idx(i + 1, j)] = fma(m10, f00[b], m11 * f01[b]);
-                D[idx(i + 1, j + 1)] = fma(m10, f10[b], m11 * f11[b]);
+                const double A2 = fa[b], B2 = fb[b], SB2 = fsb[b];
+                const double d00 = D[idx(i, j)], d01 = D[idx(i, j + 1)], d10 = D[idx(i + 1, j)], d11 = D[idx(i + 1, j + 1)];
+                const double m00 = fma(A, d00, SB * d10), m01 = fma(A, d01, SB * d11);
+                const double m10 = fma(B, d00, A * d10), m11 = fma(B, d01, A * d11);
+                D[idx(i, j)] = fma(m00, A2, m01 * SB2);
+                D[idx(i, j + 1)] = fma(m00, B2, m01 * A2);
+                D[idx(i + 1, j)] = fma(m10, A2, m11 * SB2);
+                D[idx(i + 1, j + 1)] = fma(m10, B2, m11 * A2);
             }
             if (ODD) {  // 2x1 block against the odd real root
-                double d0 = D[idx(i, P - 1)] * fo, d1 = D[idx(i + 1, P - 1)] * fo;
-                D[idx(i, P - 1)] = fma(f00[a], d0, f01[a] * d1);
-                D[idx(i + 1, P - 1)] = fma(f10[a], d0, f11[a] * d1);
+                const double d0 = D[idx(i, P - 1)] * fo, d1 = D[idx(i + 1, P - 1)] * fo;
+                D[idx(i, P - 1)] = fma(A, d0, SB * d1);
+                D[idx(i + 1, P - 1)] = fma(B, d0, A * d1);
             }
         }
         if (ODD) D[idx(P - 1, P - 1)] *= fo * fo;
 
-        // ---- predicted observation: g = D c + h, var = c.g + e2, mean = c.z
-        // __dmul_rn: never contracted into the following add, so the all-conjugate-pairs loop and the
-        // generic loop round identically (results must not depend on which lanes share a warp)
-        double m = 0.0, vv = __dmul_rn(prm.scale, e2n);
-        if (ALLC) {
-            // c = (1,0, 1,0, ..., [1]): plain sums over the first component of every slot
+        // ---- predicted observation: g = D c + h, var = c.g + e2, mean = c.z with c = (1,0,1,0,...[,1])
+        // mul_rn: never contracted into the following add, so both loop variants round identically
+        double m = z[0], vv = mul_rn(prm.scale, e2n);
 #pragma unroll
-            for (int i = 0; i < P; i++) {
-                double acc = prm.h[i];
+        for (int i = 0; i < P; i++) {
+            double acc = prm.h[i];
 #pragma unroll
-                for (int j = 0; j < P; j++)
-                    if ((j & 1) == 0) acc += D[(i <= j) ? idx(i, j) : idx(j, i)];
-                g[i] = acc;
-            }
-#pragma unroll
-            for (int i = 0; i < P; i++)
-                if ((i & 1) == 0) { vv += g[i]; m += z[i]; }
-        } else {
-#pragma unroll
-            for (int i = 0; i < P; i++) {
-                double acc = prm.h[i];
-#pragma unroll
-                for (int j = 0; j < P; j++) acc = fma(D[(i <= j) ? idx(i, j) : idx(j, i)], prm.c[j], acc);
-                g[i] = acc;
-                vv = fma(prm.c[i], acc, vv);
-                m = fma(prm.c[i], z[i], m);
-            }
+            for (int j = 0; j < P; j++)
+                if ((j & 1) == 0) acc += D[(i <= j) ? idx(i, j) : idx(j, i)];
+            g[i] = acc;
         }
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            if ((i & 1) == 0) { vv += g[i]; if (i > 0) m += z[i]; }
         var = vv;
         mean = m;
     }
 };
 
-// Running sum of -1/2 log(var_i) - 1/2 innov_i^2 / var_i with the logs folded into one log of a
-// product of mantissas (exponents summed as integers): log() leaves the time loop.
-// out-of-line: keeps the (never taken in practice) log() code out of the time loop's instruction footprint
-static __device__ __noinline__ double loglik_slow_log(double var) { return log(var); }
-
+// Running sum of -1/2 log(var_i) - 1/2 innov_i^2 / var_i with the logs folded into one log of a product of
+// mantissas (exponent fields summed as integers): log() leaves the time loop, and so does every branch -- a var
+// that is not a positive normal number only sets a sticky flag; the caller then recomputes that evaluation with
+// loglik_exact_slow (same recursion, one log() per point), which gives NaN / -inf in the same class as the reference.
 struct LogLikAcc {
     double quad;    // sum innov^2 / var
-    double prod;    // product of mantissas of var, renormalised
-    double logsum;  // direct sum of log(var) for out-of-range var (rare)
-    int esum;
-    int n_in_prod;
-    __device__ __forceinline__ void init() { quad = 0.0; prod = 1.0; logsum = 0.0; esum = 0; n_in_prod = 0; }
-    __device__ __forceinline__ void add(double var, double innov, double inv_var) {
+    double prod;    // product of mantissas of var (renormalise at least every 1000 points)
+    int esum;       // sum of biased exponent fields
+    int npts;
+    unsigned hmin, hmax;  // range of the high words of var seen so far (as unsigned: a set sign bit is "huge")
+    CARMA_HD void init() { quad = 0.0; prod = 1.0; esum = 0; npts = 0; hmin = 0x3ff00000u; hmax = 0x3ff00000u; }
+    // some var was zero, negative, subnormal, infinite or NaN: exponent field 0 or 2047, or sign set
+    CARMA_HD bool bad() const { return hmin < 0x00100000u || hmax >= 0x7ff00000u; }
+    CARMA_HD void add(double var, double innov, double inv_var) {
         quad = fma(innov * innov, inv_var, quad);
-        if (var > 1e-290 && var < 1e290) {
-            int e;
-            prod *= mantissa_and_exponent(var, &e);
-            esum += e;
-            if (++n_in_prod == 512) {  // prod < 2^512: renormalise well before overflow
-                int e2;
-                prod = mantissa_and_exponent(prod, &e2);
-                esum += e2;
-                n_in_prod = 0;
-            }
-        } else {
-            logsum += loglik_slow_log(var);  // NaN for var < 0 or NaN, -inf for 0: same class as the reference
-        }
+        const int hi = hi32(var);
+        prod *= mk64((hi & 0x000fffff) | 0x3ff00000, lo32(var));
+        esum += (int)((unsigned)hi >> 20);
+        hmin = min((unsigned)hi, hmin);
+        hmax = max((unsigned)hi, hmax);
     }
-    __device__ __forceinline__ double value() const {
-        return -0.5 * (log(prod) + (double)esum * 0.693147180559945309417232121458 + logsum) - 0.5 * quad;
+    // call at least once every 1000 add()s: prod < 2^1000
+    CARMA_HD void renorm(int added) {
+        npts += added;
+        const int hi = hi32(prod);
+        esum += (int)(((unsigned)hi >> 20) & 0x7ffu) - 1023;
+        prod = mk64((hi & 0x800fffff) | 0x3ff00000, lo32(prod));
+    }
+    CARMA_HD double value() const {
+        return -0.5 * (log(prod) + (double)(esum - 1023 * npts) * 0.693147180559945309417232121458) - 0.5 * quad;
     }
 };
 
-// Run the recursion over `len` staged points (dt, y, next-point yerr^2); the last `len - nadv`
-// (0 or 1) points are only scored, not advanced past (end of the light curve).
+// ---- where the time loop reads the light curve from
+#ifdef __CUDACC__
+// shared memory: dt[i] at a + 8 i, y[i] at a + yoff + 8 i, next-point yerr^2 at a + eoff + 8 i (device only)
+struct SeriesSmem {
+    uint32_t a, yoff, eoff;
+    __device__ __forceinline__ void get(int i, double* dt, double* y, double* e) const {
+#ifdef __CUDA_ARCH__
+        const uint32_t p = a + 8u * (uint32_t)i;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(*dt) : "r"(p));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(*y) : "r"(p + yoff));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(*e) : "r"(p + eoff));
+#endif
+    }
+    __device__ __forceinline__ double get_y(int i) const {
+        double y = 0.0;
+#ifdef __CUDA_ARCH__
+        asm("ld.shared.f64 %0, [%1];" : "=d"(y) : "r"(a + yoff + 8u * (uint32_t)i));
+#endif
+        return y;
+    }
+};
+#endif
+// global (or host) memory
+struct SeriesPtr {
+    const double* dt;
+    const double* y;
+    const double* e;
+    CARMA_HD void get(int i, double* dt_, double* y_, double* e_) const { *dt_ = dt[i]; *y_ = y[i]; *e_ = e[i]; }
+    CARMA_HD double get_y(int i) const { return y[i]; }
+};
+
+constexpr int RENORM_EVERY = 512;
+
+// Run the recursion over `len` points (dt, y, next-point yerr^2); the last `len - nadv` (0 or 1) points are
+// only scored, not advanced past (end of the light curve).
 // PF = true: the three operands of step i+1 are loaded while step i is computed (software prefetch);
 // used when the series is read straight from global memory (K4, K5), pointless for shared memory.
-template <int P, bool ALLC, bool PF = false>
-__device__ __forceinline__ void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
-                                                 const double* __restrict__ sdt, const double* __restrict__ sy,
-                                                 const double* __restrict__ se, int len, int nadv) {
+template <int P, bool ALLC, bool PF, class Src>
+CARMA_HD void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const MathTab& tb,
+                               const Src& src, int len, int nadv) {
     double y_c = 0.0, dt_c = 0.0, e_c = 0.0;
-    if (PF && len > 0) { y_c = sy[0]; dt_c = sdt[0]; e_c = se[0]; }
-    for (int i = 0; i < nadv; i++) {
-        double y_i, dt_i, e_i;
-        if (PF) {
-            y_i = y_c; dt_i = dt_c; e_i = e_c;
-            const int j = i + 1;  // j <= nadv <= len - 1 whenever the last point is only scored
-            if (j < len) { y_c = sy[j]; if (j < nadv) { dt_c = sdt[j]; e_c = se[j]; } }
-        } else {
-            y_i = sy[i]; dt_i = sdt[i]; e_i = se[i];
+    if (PF && nadv > 0) src.get(0, &dt_c, &y_c, &e_c);
+    else if (PF && len > 0) y_c = src.get_y(0);
+    for (int i0 = 0; i0 < nadv; i0 += RENORM_EVERY) {
+        const int i1 = (nadv - i0 < RENORM_EVERY) ? nadv : i0 + RENORM_EVERY;
+        for (int i = i0; i < i1; i++) {
+            double y_i, dt_i, e_i;
+            if (PF) {
+                y_i = y_c; dt_i = dt_c; e_i = e_c;
+                const int j = i + 1;  // j <= nadv <= len - 1 whenever the last point is only scored
+                if (j < nadv) src.get(j, &dt_c, &y_c, &e_c);
+                else if (j < len) y_c = src.get_y(j);
+            } else {
+                src.get(i, &dt_i, &y_i, &e_i);
+            }
+            const double innov = (y_i - prm.mu) - kf.mean;
+            const double inv = rcp_fast(kf.var);
+            acc.add(kf.var, innov, inv);
+            kf.template advance<ALLC>(prm, tb, innov, inv, dt_i, e_i);
         }
-        double innov = (y_i - prm.mu) - kf.mean;
-        double inv = rcp_fast(kf.var);
-        acc.add(kf.var, innov, inv);
-        kf.template advance<ALLC>(prm, innov, inv, dt_i, e_i);
+        acc.renorm(i1 - i0);
     }
     if (nadv < len) {
-        double y_l = PF ? y_c : sy[len - 1];
-        double innov = (y_l - prm.mu) - kf.mean;
-        double inv = rcp_fast(kf.var);
+        const double y_l = PF ? y_c : src.get_y(len - 1);
+        const double innov = (y_l - prm.mu) - kf.mean;
+        const double inv = rcp_fast(kf.var);
         acc.add(kf.var, innov, inv);
+        acc.renorm(1);
     }
 }
 
-template <int P, bool PF>
-__device__ __forceinline__ void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
-                                                const double* __restrict__ sdt, const double* __restrict__ sy,
-                                                const double* __restrict__ se, int len, int nadv) {
+template <int P, bool PF, class Src>
+CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const MathTab& tb,
+                              const Src& src, int len, int nadv) {
     constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
-    // Warp-uniform choice: the straight-line all-conjugate-pairs loop only when EVERY active lane of the
-    // warp qualifies; otherwise all lanes run the generic loop (per-slot selection, reconverging each
-    // slot).  A per-lane choice would execute both loops back to back in a mixed warp.
+#ifdef __CUDA_ARCH__
+    // Warp-uniform choice: the all-conjugate-pairs loop (no per-lane selections) only when EVERY active lane of
+    // the warp qualifies; otherwise all lanes run the generic loop.  Both round identically on a conjugate pair,
+    // so a result never depends on which lanes share a warp.
     const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
-    if (all_c) filter_span_impl<P, true, PF>(kf, acc, prm, sdt, sy, se, len, nadv);
-    else filter_span_impl<P, false, PF>(kf, acc, prm, sdt, sy, se, len, nadv);
+#else
+    const bool all_c = prm.cmask == ALL;
+#endif
+    if (all_c) filter_span_impl<P, true, PF>(kf, acc, prm, tb, src, len, nadv);
+    else filter_span_impl<P, false, PF>(kf, acc, prm, tb, src, len, nadv);
 }
 
-template <int P>
-__device__ __forceinline__ void filter_span(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm,
-                                            const double* __restrict__ sdt, const double* __restrict__ sy,
-                                            const double* __restrict__ se, int len, int nadv) {
-    filter_span_any<P, false>(kf, acc, prm, sdt, sy, se, len, nadv);
+// Exact (slow) evaluation of the log-likelihood of one theta: the same recursion with one log() per point.
+// Only reached when LogLikAcc::bad was raised (var not a positive normal number somewhere).
+template <int P, class Src>
+__host__ __device__ __noinline__ double loglik_exact_slow(const RealParams<P>& prm, const MathTab& tb, const Src& src,
+                                                          int ny, double e2_0) {
+    KalmanReal<P> kf;
+    kf.reset(prm, e2_0);
+    double ll = 0.0;
+    for (int i = 0; i < ny; i++) {
+        double dt_i = 0.0, y_i, e_i = 0.0;
+        if (i + 1 < ny) src.get(i, &dt_i, &y_i, &e_i);
+        else y_i = src.get_y(i);
+        const double innov = (y_i - prm.mu) - kf.mean;
+        ll += -0.5 * log(kf.var) - 0.5 * innov * innov / kf.var;
+        if (i + 1 < ny) kf.template advance<false>(prm, tb, innov, 1.0 / kf.var, dt_i, e_i);
+    }
+    return ll;
 }
 
 }  // namespace carma

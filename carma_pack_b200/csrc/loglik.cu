@@ -21,6 +21,7 @@ namespace carma {
 // K1
 // ---------------------------------------------------------------------------------------------
 constexpr int K1_BLOCK = 64;
+constexpr int K1_CHUNK = 512;  // points per staged chunk: compile-time strides, so the loop's three LDS share one address register
 
 // resident blocks per SM wanted for each P (bounds the register allocation so that the
 // BASELINE batch of 65,536 thetas fits in one wave of 148 SMs: 7 x 64 x 148 = 66,304 at P = 5)
@@ -29,33 +30,35 @@ __host__ __device__ constexpr int k1_min_blocks(int P) { return P <= 4 ? 8 : (P 
 template <int P>
 __global__ void __launch_bounds__(K1_BLOCK, k1_min_blocks(P))
 loglik_batch_kernel(SeriesView sv, int kind, int q, int d, unsigned flags, carma_prior_t prior,
-                    const double* __restrict__ theta, double* __restrict__ out, size_t n, int chunk) {
+                    const double* __restrict__ theta, double* __restrict__ out, size_t n) {
+    // series chunk buffers, aliased with the LU scratch of the prologue (the math tables are static shared arrays)
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bars[2];
 
     const int tid = threadIdx.x;
     const size_t row = (size_t)blockIdx.x * K1_BLOCK + tid;
     const int ny = sv.ny;
-    const int nchunks = (ny + chunk - 1) / chunk;
-    const int nbuf = nchunks > 1 ? 2 : 1;
+    const int nchunks = (ny + K1_CHUNK - 1) / K1_CHUNK;
+    double* work = smem;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
-    __syncthreads();
+    MathTab tb;
+    tb.load();  // ends with __syncthreads()
 
     auto issue = [&](int k) {
         // chunk k -> buffer k&1 : three bulk copies (dt, y, e2n), byte counts multiples of 16
-        int start = k * chunk;
-        int len = min(chunk, sv.nyp - start);
-        uint32_t bytes = (uint32_t)len * 8u;
-        double* dst = smem + (size_t)(k & 1) * 3 * chunk;
+        const int start = k * K1_CHUNK;
+        const int len = min(K1_CHUNK, sv.nyp - start);
+        const uint32_t bytes = (uint32_t)len * 8u;
+        double* dst = work + (size_t)(k & 1) * 3 * K1_CHUNK;
         mbar_expect_tx(&bars[k & 1], 3u * bytes);
         bulk_g2s(dst, sv.dt + start, bytes, &bars[k & 1]);
-        bulk_g2s(dst + chunk, sv.y + start, bytes, &bars[k & 1]);
-        bulk_g2s(dst + 2 * chunk, sv.e2n + start, bytes, &bars[k & 1]);
+        bulk_g2s(dst + K1_CHUNK, sv.y + start, bytes, &bars[k & 1]);
+        bulk_g2s(dst + 2 * K1_CHUNK, sv.e2n + start, bytes, &bars[k & 1]);
     };
 
     // ---- per-theta prologue.  The P x P complex LU of the Vandermonde solve works in shared memory
@@ -67,34 +70,31 @@ loglik_batch_kernel(SeriesView sv, int kind, int q, int d, unsigned flags, carma
     int status = TT_OK;
     if (active) {
         // theta is read straight from global memory (the transform touches only its first d entries)
-        status = transform_theta<P, false, true>(kind, q, flags, prior, theta + row * (size_t)d, prm, nullptr, smem + tid,
-                                                 K1_BLOCK);
+        status = transform_theta<P, false, true>(kind, q, flags, prior, theta + row * (size_t)d, sv.dt_max, prm, nullptr,
+                                                 work + tid, K1_BLOCK);
         if (status != TT_OK) active = false;
     }
-    if (active) {
-        kf.reset(prm, sv.e2_0);
-        acc.init();
-    }
+    if (active) kf.reset(prm, sv.e2_0);
+    acc.init();
     // the generic-proxy accesses above must be ordered before the bulk (async-proxy) writes into the same bytes
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
         issue(0);
-        if (nbuf > 1) issue(1);
+        if (nchunks > 1) issue(1);
     }
 
     // ---- time loop
+    const uint32_t work_addr = smem_u32(work);
     for (int k = 0; k < nchunks; k++) {
         const int buf = k & 1;
         mbar_wait(&bars[buf], (uint32_t)((k >> 1) & 1));
         if (active) {
-            const double* sdt = smem + (size_t)buf * 3 * chunk;
-            const double* sy = sdt + chunk;
-            const double* se = sdt + 2 * chunk;
-            const int start = k * chunk;
-            const int len = min(chunk, ny - start);
+            const SeriesSmem src{work_addr + (uint32_t)buf * 3u * K1_CHUNK * 8u, K1_CHUNK * 8u, 2u * K1_CHUNK * 8u};
+            const int start = k * K1_CHUNK;
+            const int len = min(K1_CHUNK, ny - start);
             const int nadv = (start + len == ny) ? len - 1 : len;  // no advance after the last point
-            filter_span<P>(kf, acc, prm, sdt, sy, se, len, nadv);
+            filter_span_any<P, false>(kf, acc, prm, tb, src, len, nadv);
         }
         if (k + 2 < nchunks) {
             __syncthreads();  // every thread is done with this buffer
@@ -105,26 +105,31 @@ loglik_batch_kernel(SeriesView sv, int kind, int q, int d, unsigned flags, carma
     if (row < n) {
         double r;
         if (status != TT_OK) r = -INFINITY;
+        else if (acc.bad()) r = loglik_exact_slow<P>(prm, tb, SeriesPtr{sv.dt, sv.y, sv.e2n}, ny, sv.e2_0) + prm.logprior;
         else r = acc.value() + prm.logprior;
         out[row] = r;
     }
 }
 
+static size_t k1_smem_bytes(int P, int ny) {
+    const int nchunks = (ny + K1_CHUNK - 1) / K1_CHUNK;
+    size_t series = (size_t)(nchunks > 1 ? 2 : 1) * 3 * K1_CHUNK * sizeof(double);
+    size_t lu = (size_t)2 * P * P * K1_BLOCK * sizeof(double);  // LU scratch of the prologue (aliased)
+    return std::max(series, lu);
+}
+
 template <int P>
 static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsigned flags, const carma_prior_t& prior,
                              const double* d_theta, double* d_out, size_t n, cudaStream_t stream) {
-    int chunk = std::min(sv.nyp, 512);
-    int nchunks = (sv.ny + chunk - 1) / chunk;
-    size_t smem = (size_t)(nchunks > 1 ? 2 : 1) * 3 * chunk * sizeof(double);
-    smem = std::max(smem, (size_t)2 * P * P * K1_BLOCK * sizeof(double));  // LU scratch of the prologue (aliased)
+    const size_t smem = k1_smem_bytes(P, sv.ny);
     unsigned grid = (unsigned)((n + K1_BLOCK - 1) / K1_BLOCK);
     if (smem > 48 * 1024) {
-        // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 50,176 B).  Per device and always the same
+        // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 54,528 B).  Per device and always the same
         // value, so concurrent callers cannot disagree.
         cudaError_t e = cudaFuncSetAttribute(loglik_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
     }
-    loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n, chunk);
+    loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n);
     return cudaGetLastError();
 }
 
@@ -152,9 +157,11 @@ constexpr int K4_BLOCK = 64;
 template <int P>
 __global__ void __launch_bounds__(K4_BLOCK)
 multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y, const double* __restrict__ e2,
-                    const long long* __restrict__ off, size_t ncurves, int kind, int q, int d, unsigned flags,
+                    const long long* __restrict__ off, size_t ncurves, double dt_max, int kind, int q, int d, unsigned flags,
                     const carma_prior_t* __restrict__ priors, const double* __restrict__ theta,
                     double* __restrict__ out) {
+    MathTab tb;
+    tb.load();
     const size_t c = (size_t)blockIdx.x * K4_BLOCK + threadIdx.x;
     if (c >= ncurves) return;
     const long long o0 = off[c], o1 = off[c + 1];
@@ -164,7 +171,7 @@ multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y,
     for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[c * (size_t)d + j] : 0.0;
     RealParams<P> prm;
     carma_prior_t pr = priors[c];
-    int status = transform_theta<P>(kind, q, flags, pr, th, prm);
+    int status = transform_theta<P>(kind, q, flags, pr, th, dt_max, prm);
     if (status != TT_OK || ny <= 0) {
         out[c] = (ny <= 0) ? 0.0 : -INFINITY;
         return;
@@ -174,8 +181,9 @@ multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y,
     kf.reset(prm, e2[o0]);
     acc.init();
     // e2 of the NEXT point is needed at step i: pass the array shifted by one
-    filter_span_any<P, true>(kf, acc, prm, dt + o0, y + o0, e2 + o0 + 1, ny, ny - 1);
-    out[c] = acc.value() + prm.logprior;
+    const SeriesPtr src{dt + o0, y + o0, e2 + o0 + 1};
+    filter_span_any<P, true>(kf, acc, prm, tb, src, ny, ny - 1);
+    out[c] = (acc.bad() ? loglik_exact_slow<P>(prm, tb, src, ny, e2[o0]) : acc.value()) + prm.logprior;
 }
 
 cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, int q, unsigned flags,
@@ -184,8 +192,8 @@ cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, in
     int d = model_dim(kind, p, q);
     unsigned grid = (unsigned)((m->ncurves + K4_BLOCK - 1) / K4_BLOCK);
 #define LAUNCH_K4(PP)                                                                                             \
-    multi_loglik_kernel<PP><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, kind, q, \
-                                                           d, flags, d_priors, d_theta, d_out)
+    multi_loglik_kernel<PP><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, m->dt_max, \
+                                                           kind, q, d, flags, d_priors, d_theta, d_out)
     switch (p) {
         case 1: LAUNCH_K4(1); break;
         case 2: LAUNCH_K4(2); break;
@@ -299,16 +307,24 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     if (s == 12345.678) out[0] = s;
 }
 
-__global__ void fastmath_kernel(const double* __restrict__ x, size_t n, double* __restrict__ e, double* __restrict__ sn,
-                                double* __restrict__ cs, double* __restrict__ rc) {
+__global__ void fastmath_kernel(const double* __restrict__ l, const double* __restrict__ dt, size_t n, double* __restrict__ e,
+                                double* __restrict__ sn, double* __restrict__ cs, double* __restrict__ sr, double* __restrict__ cr,
+                                double* __restrict__ rc) {
+    MathTab tb;
+    tb.load();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    e[i] = exp_fast(x[i]);
-    double s, c;
-    sincos_fast(x[i], &s, &c);
+    e[i] = exp_scaled(l[i], dt[i], tb);
+    double s, c, s1, c1;
+    rot_scaled<true>(l[i], dt[i], true, tb, &s, &c);
+    rot_scaled<false>(l[i], dt[i], true, tb, &s1, &c1);
+    if (s1 != s || c1 != c) s = NAN;  // the all-conjugate and the generic variant must agree bit for bit
     sn[i] = s;
     cs[i] = c;
-    rc[i] = rcp_fast(x[i]);
+    rot_scaled<false>(l[i], dt[i], false, tb, &s, &c);
+    sr[i] = s;
+    cr[i] = c;
+    rc[i] = rcp_fast(l[i]);
 }
 
 __global__ void philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out) {
@@ -419,6 +435,8 @@ int carma_series_create(const double* time, const double* y, const double* yerr,
     s->yerr.assign(yerr, yerr + ny);
     s->st = compute_stats(time, y, ny);
     s->e2_0 = yerr[0] * yerr[0];
+    s->dt_max = 0.0;
+    for (size_t i = 0; i + 1 < ny; i++) s->dt_max = std::max(s->dt_max, time[i + 1] - time[i]);
     std::vector<double> pack(3 * (size_t)s->nyp + ny, 0.0);
     for (size_t i = 0; i < ny; i++) {
         pack[i] = (i + 1 < ny) ? time[i + 1] - time[i] : 0.0;
@@ -536,7 +554,7 @@ int carma_multi_series_create(const double* time, const double* y, const double*
     size_t total = (size_t)offsets[ncurves];
     carma_multi_series* m = new (std::nothrow) carma_multi_series();
     if (!m) return CARMA_ERR_ALLOC;
-    m->device = device; m->ncurves = ncurves; m->total = total;
+    m->device = device; m->ncurves = ncurves; m->total = total; m->dt_max = 0.0;
     m->off.assign(offsets, offsets + ncurves + 1);
     m->priors_pop.resize(ncurves); m->priors_sample.resize(ncurves);
     std::vector<double> dt(total + 1, 0.0), e2(total + 1, 0.0);
@@ -547,6 +565,7 @@ int carma_multi_series_create(const double* time, const double* y, const double*
         for (size_t i = o0; i < o1; i++) {
             if (i + 1 < o1) {
                 dt[i] = time[i + 1] - time[i];
+                m->dt_max = std::max(m->dt_max, dt[i]);
                 if (!(dt[i] > 0)) { set_error("carma_multi_series_create: times must be strictly increasing within a curve"); delete m; return CARMA_ERR_ARG; }
             }
             e2[i] = yerr[i] * yerr[i];
@@ -712,19 +731,20 @@ int carma_fp64_peak_tflops(int device, double* tflops) {
     return CARMA_OK;
 }
 
-int carma_fastmath_dev(const double* x, size_t n, double* out_exp, double* out_sin, double* out_cos, double* out_rcp) {
-    if (!x || !out_exp || !out_sin || !out_cos || !out_rcp) return CARMA_ERR_ARG;
+int carma_fastmath_dev(const double* rate, const double* dt, size_t n, double* out_exp, double* out_sin, double* out_cos,
+                       double* out_sh, double* out_ch, double* out_rcp) {
+    if (!rate || !dt || !out_exp || !out_sin || !out_cos || !out_sh || !out_ch || !out_rcp) return CARMA_ERR_ARG;
     if (n == 0) return CARMA_OK;
     double* d = nullptr;
-    if (!cuda_ok(cudaMalloc((void**)&d, 5 * n * sizeof(double)), "cudaMalloc")) return CARMA_ERR_CUDA;
-    bool ok = cuda_ok(cudaMemcpy(d, x, n * sizeof(double), cudaMemcpyHostToDevice), "H2D x");
+    if (!cuda_ok(cudaMalloc((void**)&d, 8 * n * sizeof(double)), "cudaMalloc")) return CARMA_ERR_CUDA;
+    bool ok = cuda_ok(cudaMemcpy(d, rate, n * sizeof(double), cudaMemcpyHostToDevice), "H2D rate") &&
+              cuda_ok(cudaMemcpy(d + n, dt, n * sizeof(double), cudaMemcpyHostToDevice), "H2D dt");
     if (ok) {
-        fastmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, n, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
-        ok = cuda_ok(cudaGetLastError(), "fastmath_kernel launch") &&
-             cuda_ok(cudaMemcpy(out_exp, d + n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
-             cuda_ok(cudaMemcpy(out_sin, d + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
-             cuda_ok(cudaMemcpy(out_cos, d + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H") &&
-             cuda_ok(cudaMemcpy(out_rcp, d + 4 * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H");
+        fastmath_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d, d + n, n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, d + 6 * n, d + 7 * n);
+        double* outs[6] = {out_exp, out_sin, out_cos, out_sh, out_ch, out_rcp};
+        ok = cuda_ok(cudaGetLastError(), "fastmath_kernel launch");
+        for (int k = 0; k < 6 && ok; k++)
+            ok = cuda_ok(cudaMemcpy(outs[k], d + (2 + k) * n, n * sizeof(double), cudaMemcpyDeviceToHost), "D2H");
     }
     cudaFree(d);
     return ok ? CARMA_OK : CARMA_ERR_CUDA;

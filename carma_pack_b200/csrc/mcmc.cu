@@ -52,6 +52,7 @@ struct PTParams {
     unsigned long long n_ens;
     // series statistics for the starting values
     double y_mean, y_var_sample, y_var_pop, median_dt, tspan;
+    double dt_max;       // longest gap of the series (all curves in multi mode): rate clamp of transform_theta
     int ny;
     int series_in_smem;  // 1: sdt/sy/se of the log-density calls point into shared memory
     // device buffers
@@ -138,28 +139,29 @@ __device__ void starting_ar(StartRng& g, const PTParams& pp, double* loga) {
 // __noinline__: one copy of the filter loop per kernel (three call sites), with its own register
 // allocation, so the MCMC bookkeeping around it does not inflate the per-thread register count.
 template <int P>
-__device__ __noinline__ double logdensity_resident(const PTParams& pp, const double* th, const double* sdt,
+__device__ __noinline__ double logdensity_resident(const PTParams& pp, const MathTab& tb, const double* th, const double* sdt,
                                                    const double* sy, const double* se, double e2_0) {
     RealParams<P> prm;
-    if (transform_theta<P>(pp.kind, pp.q, 0u, pp.prior, th, prm) != TT_OK) return -INFINITY;
+    if (transform_theta<P>(pp.kind, pp.q, 0u, pp.prior, th, pp.dt_max, prm) != TT_OK) return -INFINITY;
     KalmanReal<P> kf;
     LogLikAcc acc;
     kf.reset(prm, e2_0);
     acc.init();
+    const SeriesPtr gsrc{sdt, sy, se};
     if (pp.series_in_smem) {
-        // tell the compiler the address space: LDS with a uniform address instead of generic loads
-        __builtin_assume(__isShared(sdt));
-        __builtin_assume(__isShared(sy));
-        __builtin_assume(__isShared(se));
-        filter_span_any<P, false>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+        // the staged series: LDS off one 32-bit address register
+        const uint32_t a = smem_u32(sdt);
+        const SeriesSmem src{a, smem_u32(sy) - a, smem_u32(se) - a};
+        filter_span_any<P, false>(kf, acc, prm, tb, src, pp.ny, pp.ny - 1);
     } else {
-        filter_span_any<P, true>(kf, acc, prm, sdt, sy, se, pp.ny, pp.ny - 1);
+        filter_span_any<P, true>(kf, acc, prm, tb, gsrc, pp.ny, pp.ny - 1);
     }
+    if (acc.bad()) return loglik_exact_slow<P>(prm, tb, gsrc, pp.ny, e2_0) + prm.logprior;
     return acc.value() + prm.logprior;
 }
 
 template <int P>
-__device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double* th, const double* sdt,
+__device__ double starting_value_attempt(const PTParams& pp, const MathTab& tb, StartRng& g, double* th, const double* sdt,
                                          const double* sy, const double* se, double e2_0) {
     const int n = pp.ny;
     if (pp.kind == CARMA_KIND_CAR1) {
@@ -170,7 +172,7 @@ __device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double
         double scale = g.scaled_inverse_chisqr((int)pp.prior.measerr_dof, 1.0);
         scale = fmax(fmin(scale, 1.99), 0.51);
         th[0] = sd; th[1] = scale; th[2] = mu; th[3] = log_omega;
-        return logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
+        return logdensity_resident<P>(pp, tb, th, sdt, sy, se, e2_0);
     }
     starting_ar<P>(g, pp, th + 3);
     if (pp.kind == CARMA_KIND_CARMA)
@@ -184,7 +186,7 @@ __device__ double starting_value_attempt(const PTParams& pp, StartRng& g, double
     double scale = g.scaled_inverse_chisqr((int)pp.prior.measerr_dof, 1.0);
     scale = fmax(fmin(scale, 1.99), 0.51);
     th[0] = sqrt(yvar); th[1] = scale; th[2] = mu;
-    return logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
+    return logdensity_resident<P>(pp, tb, th, sdt, sy, se, e2_0);
 }
 
 __device__ __forceinline__ int tri(int k, int j) { return j * (j + 1) / 2 + k; }  // k <= j
@@ -208,13 +210,16 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
     bool active;
     const int nyp = mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0;
 
+    // [ dt | y | e2n | exchange area ] (the math tables are static shared arrays)
     double* sdt = smem;
-    double* sy = smem + nyp;
-    double* se = smem + 2 * (size_t)nyp;
-    double* xth = smem + 3 * (size_t)nyp + 2;          // [PT_BLOCK][d] exchange area
+    double* sy = sdt + nyp;
+    double* se = sdt + 2 * (size_t)nyp;
+    double* xth = sdt + 3 * (size_t)nyp + 2;           // [PT_BLOCK][d] exchange area
     double* xlp = xth + (size_t)PT_BLOCK * d;           // [PT_BLOCK]
     double* xu = xlp + PT_BLOCK;                        // [PT_BLOCK] exchange uniforms
     double e2_0;
+    MathTab tb;
+    tb.load();  // ends with __syncthreads()
     if (mm.enabled) {
         // ---- this block's curve: coalesced cooperative copy (ragged offsets are not 16-byte aligned,
         // so no bulk copy here); se is the yerr^2 array shifted by one point
@@ -296,13 +301,13 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         bool ok = false;
         if (pp.init) {
             for (int j = 0; j < d; j++) th[j] = pp.init[j];
-            lp = logdensity_resident<P>(pp, th, sdt, sy, se, e2_0);
+            lp = logdensity_resident<P>(pp, tb, th, sdt, sy, se, e2_0);
             ok = isfinite(lp);
         }
         if (!ok) {
             for (int a = 0; a < pp.max_start && !ok; a++) {
                 StartRng g{pp.seed, chain, (uint32_t)a, 0u};
-                lp = starting_value_attempt<P>(pp, g, th, sdt, sy, se, e2_0);
+                lp = starting_value_attempt<P>(pp, tb, g, th, sdt, sy, se, e2_0);
                 ok = isfinite(lp);
             }
         }
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
                 nv[j] = th[j] + s;
             }
             for (int j = d; j < MAX_D; j++) nv[j] = 0.0;
-            const double lpn = logdensity_resident<P>(pp, nv, sdt, sy, se, e2_0);
+            const double lpn = logdensity_resident<P>(pp, tb, nv, sdt, sy, se, e2_0);
             // ---- Accept (steps.cpp:36-56)
             double alpha = (lpn - lp) / temp;
             double u = NAN;
@@ -407,8 +412,10 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
                     const double tcm = exp(log(pp.tmax) * (double)(c - 1) / (double)(T - 1));
                     const double this_lp = xlp[base + c], other_lp = xlp[base + c - 1];
                     double a = 1.0 / tc * (other_lp - this_lp) + 1.0 / tcm * (this_lp - other_lp);
-                    a = fmin(exp(a), 1.0);
-                    if (!isfinite(a)) a = 0.0;
+                    // std::min(exp(a), 1.0) keeps a NaN (steps.hpp:334-337 then sets alpha = 0); CUDA's fmin would
+                    // return the non-NaN operand, i.e. 1 -> always swap: test before the clamp
+                    const double ea = exp(a);
+                    a = (ea == ea) ? fmin(ea, 1.0) : 0.0;
                     const double ux = xu[base + c];
                     const bool sw = ux < a;
                     if (sw) {
@@ -546,6 +553,7 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         pp.n_ens = n_ensembles;
         pp.y_mean = s->st.mean; pp.y_var_sample = s->st.var_sample; pp.y_var_pop = s->st.var_pop;
         pp.median_dt = s->st.median_dt; pp.tspan = s->st.tmax - s->st.tmin; pp.ny = (int)s->ny;
+        pp.dt_max = s->dt_max;
         grid = (unsigned)((n_ensembles + epb - 1) / epb);
         scratch = &s->scratch_misc;
     } else {
@@ -556,6 +564,7 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         mm.max_nyp = (m->max_ny + 1) & ~1;
         mm.ens_per_curve = n_ensembles;
         pp.n_ens = n_ensembles * m->ncurves;
+        pp.dt_max = m->dt_max;
         grid = (unsigned)(m->ncurves * (size_t)mm.blocks_per_curve);
         scratch = &m->scratch_misc;
     }

@@ -168,9 +168,11 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
     std::vector<double> S((size_t)m * n * d), Y((size_t)m * n * d), alpha((size_t)m * n), rho((size_t)m * n), ftmp(n * d);
     std::vector<char> active(n), todo(n), moved(n), blocked(n * d), grad_done(n);
     std::vector<double> fbig(n * (d + 4));
-    std::vector<size_t> rows;
-    int nhist = 0;  // history entries in use; entry h lives at slot (hist0 + h) % m, oldest first
-    int hist0 = 0;
+    std::vector<size_t> rows, retry;
+    // History is kept PER ROW: row i has nh[i] pairs, pair h (oldest first) in ring slot (h0[i] + h) % m.  A row
+    // whose newest (s, y) fails the curvature test simply keeps its previous pairs, so the result of a start never
+    // depends on which other starts share the batch (and hence not on how the starts are sharded over GPUs).
+    std::vector<int> nh(n, 0), h0(n, 0);
 
     for (size_t i = 0; i < n; i++)
         for (size_t j = 0; j < d; j++) x[i * d + j] = std::min(std::max(x0[i * d + j], lower[j]), upper[j]);
@@ -188,11 +190,37 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
         int rc = ev.run(k, ftmp.data());
         if (rc) return rc;
         k = 0;
+        retry.clear();
         for (size_t i : rr)
             for (size_t j = 0; j < d; j++, k++) {
                 double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
-                gout[i * d + j] = (std::fabs(ftmp[k]) >= BIG) ? 0.0 : (ftmp[k] - fz[i]) / h;
+                if (std::fabs(ftmp[k]) >= BIG) { gout[i * d + j] = 0.0; retry.push_back(i * d + j); }
+                else gout[i * d + j] = (ftmp[k] - fz[i]) / h;
             }
+        if (retry.empty()) return CARMA_OK;
+        // the perturbed point has no finite value (it left the support of the density): difference the other way
+        // before giving the component up, so that a start next to a prior bound is not mistaken for a stationary
+        // point.  If the other side is infeasible too the component stays 0.
+        k = 0;
+        for (size_t ij : retry) {
+            const size_t i = ij / d, j = ij % d;
+            std::memcpy(ev.in + k * d, &z[i * d], d * sizeof(double));
+            const double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+            const double hb = -h;
+            if (z[i * d + j] + hb >= lower[j] && z[i * d + j] + hb <= upper[j]) ev.in[k * d + j] += hb;
+            k++;
+        }
+        rc = ev.run(k, ftmp.data());
+        if (rc) return rc;
+        k = 0;
+        for (size_t ij : retry) {
+            const size_t i = ij / d, j = ij % d;
+            const double h = (z[i * d + j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
+            const double hb = -h;
+            const bool stepped = z[i * d + j] + hb >= lower[j] && z[i * d + j] + hb <= upper[j];
+            if (stepped && std::fabs(ftmp[k]) < BIG) gout[ij] = (ftmp[k] - fz[i]) / hb;
+            k++;
+        }
         return CARMA_OK;
     };
 
@@ -227,6 +255,7 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
             double* qi = &qv[i * d];
             const double* pgi = &pg[i * d];
             for (size_t j = 0; j < d; j++) qi[j] = pgi[j];
+            const int nhist = nh[i], hist0 = h0[i];
             for (int h = nhist - 1; h >= 0; h--) {
                 const size_t sl = (size_t)((hist0 + h) % m);
                 const double *sv = &S[(sl * n + i) * d], *yv = &Y[(sl * n + i) * d];
@@ -316,12 +345,14 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
                     fn[i] = fr[hit];
                     todo[i] = 0;
                     if (spec && hit == 0) {
+                        bool all_finite = true;
                         for (size_t j = 0; j < d; j++) {
                             const double h = (base[j] + o.fd_eps > upper[j]) ? -o.fd_eps : o.fd_eps;
                             const double fv = fr[(size_t)nt + j];
-                            gn[i * d + j] = (std::fabs(fv) >= BIG) ? 0.0 : (fv - fn[i]) / h;
+                            if (std::fabs(fv) >= BIG) all_finite = false;
+                            gn[i * d + j] = (fv - fn[i]) / h;
                         }
-                        grad_done[i] = 1;
+                        grad_done[i] = all_finite;  // otherwise grad() below redoes the row with its backward retry
                     }
                 } else {
                     for (int c = 0; c < nt; c++) t[i] *= 0.5;
@@ -339,34 +370,22 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
             rc = grad(rows, xn, fn, gn);
             if (rc) return rc;
         }
-        // history update: rows without positive curvature contribute zero vectors
-        bool any_curv = false;
-        const size_t slnew = (size_t)((hist0 + nhist) % m);  // slot that would receive the new pair
-        std::vector<double>& Sn = ftmp;                        // reuse as scratch of size n*d for s; y goes to qv
+        // history update, row by row: a pair enters a row's ring only if that row moved and s.y > 0
         for (size_t i = 0; i < n; i++) {
+            if (!moved[i]) continue;
             double sy = 0.0;
-            for (size_t j = 0; j < d; j++) {
-                const double sv = moved[i] ? xn[i * d + j] - x[i * d + j] : 0.0;
-                const double yv = moved[i] ? gn[i * d + j] - g[i * d + j] : 0.0;
-                Sn[i * d + j] = sv;
-                qv[i * d + j] = yv;
-                sy += sv * yv;
-            }
-            const bool curv = sy > 1e-12;
-            any_curv = any_curv || curv;
-            if (!curv)
-                for (size_t j = 0; j < d; j++) { Sn[i * d + j] = 0.0; qv[i * d + j] = 0.0; }
-        }
-        if (any_curv) {
-            size_t dst = slnew;
-            if (nhist == m) {  // drop the oldest
-                dst = (size_t)hist0;
-                hist0 = (hist0 + 1) % m;
+            for (size_t j = 0; j < d; j++) sy += (xn[i * d + j] - x[i * d + j]) * (gn[i * d + j] - g[i * d + j]);
+            if (!(sy > 1e-12)) continue;
+            size_t dst;
+            if (nh[i] == m) {  // drop the oldest
+                dst = (size_t)h0[i];
+                h0[i] = (h0[i] + 1) % m;
             } else {
-                nhist++;
+                dst = (size_t)((h0[i] + nh[i]) % m);
+                nh[i]++;
             }
-            std::memcpy(&S[dst * n * d], Sn.data(), n * d * sizeof(double));
-            std::memcpy(&Y[dst * n * d], qv.data(), n * d * sizeof(double));
+            double *sv = &S[(dst * n + i) * d], *yv = &Y[(dst * n + i) * d];
+            for (size_t j = 0; j < d; j++) { sv[j] = xn[i * d + j] - x[i * d + j]; yv[j] = gn[i * d + j] - g[i * d + j]; }
         }
         for (size_t i = 0; i < n; i++) {
             const bool small = moved[i] && ((f[i] - fn[i]) <= o.ftol * std::max(std::max(std::fabs(f[i]), std::fabs(fn[i])), 1.0));

@@ -45,7 +45,7 @@ struct FiltState {
 };
 
 template <int P>
-__global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma_prior_t prior,
+__global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma_prior_t prior, double dt_max,
                                    const double* __restrict__ theta, ScanParams<P>* __restrict__ out, int nrows) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
@@ -55,7 +55,7 @@ __global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma
     for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta[j] : 0.0;
     double Vr[P * (P + 1) / 2];
     RealParams<P> prm;
-    int st = transform_theta<P, true>(kind, q, flags, prior, th, prm, Vr);
+    int st = transform_theta<P, true>(kind, q, flags, prior, th, dt_max, prm, Vr);
     out->status = st;
     out->prm = prm;
     int o = 0;
@@ -63,32 +63,27 @@ __global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma
         for (int n = m; n < P; n++) { out->V[m][n] = Vr[o]; out->V[n][m] = Vr[o]; o++; }
 }
 
-// dense transition matrix Phi(dt) in the real basis
+// dense transition matrix Phi(dt) in the real basis: 2x2 blocks [[A, sB],[B, A]] (kalman_real.cuh)
 template <int P>
-__device__ void build_phi(const RealParams<P>& prm, double dt, double F[P][P]) {
+__device__ void build_phi(const RealParams<P>& prm, const MathTab& tb, double dt, double F[P][P]) {
     for (int i = 0; i < P; i++)
         for (int j = 0; j < P; j++) F[i][j] = 0.0;
-    for (int s = 0; s < P / 2; s++) {
-        double e = exp_fast(prm.lam[2 * s] * dt);
-        if ((prm.cmask >> s) & 1u) {
-            double sn, cs;
-            sincos_fast(prm.lam[2 * s + 1] * dt, &sn, &cs);
-            F[2 * s][2 * s] = e * cs; F[2 * s][2 * s + 1] = -(e * sn);
-            F[2 * s + 1][2 * s] = e * sn; F[2 * s + 1][2 * s + 1] = e * cs;
-        } else {
-            F[2 * s][2 * s] = e;
-            F[2 * s + 1][2 * s + 1] = exp_fast(prm.lam[2 * s + 1] * dt);
-        }
+    constexpr int NS = P / 2;
+    double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
+    KalmanReal<P>::template transition<false>(prm, tb, dt, fa, fb, fsb, &fo);
+    for (int s = 0; s < NS; s++) {
+        F[2 * s][2 * s] = fa[s]; F[2 * s][2 * s + 1] = fsb[s];
+        F[2 * s + 1][2 * s] = fb[s]; F[2 * s + 1][2 * s + 1] = fa[s];
     }
-    if (P & 1) F[P - 1][P - 1] = exp_fast(prm.lam[P - 1] * dt);
+    if (P & 1) F[P - 1][P - 1] = fo;
 }
 
 // per-point quantities of point k >= 1 reached from k-1 by dt:  Q = V - F V F^T, w = F^T c, Qc, S, K
 template <int P>
 struct StepOps {
     double F[P][P], Q[P][P], w[P], Qc[P], K[P], S;
-    __device__ void build(const ScanParams<P>& sp, double dt, double r) {
-        build_phi<P>(sp.prm, dt, F);
+    __device__ void build(const ScanParams<P>& sp, const MathTab& tb, double dt, double r) {
+        build_phi<P>(sp.prm, tb, dt, F);
         double FV[P][P];
         for (int i = 0; i < P; i++)
             for (int j = 0; j < P; j++) {
@@ -105,11 +100,11 @@ struct StepOps {
         S = r;
         for (int i = 0; i < P; i++) {
             double a = 0.0, q = 0.0;
-            for (int k = 0; k < P; k++) { a = fma(F[k][i], sp.prm.c[k], a); q = fma(Q[i][k], sp.prm.c[k], q); }
+            for (int k = 0; k < P; k++) { a = fma(F[k][i], obs_c<P>(k), a); q = fma(Q[i][k], obs_c<P>(k), q); }
             w[i] = a;
             Qc[i] = q;
         }
-        for (int i = 0; i < P; i++) S = fma(sp.prm.c[i], Qc[i], S);
+        for (int i = 0; i < P; i++) S = fma(obs_c<P>(i), Qc[i], S);
         for (int i = 0; i < P; i++) K[i] = Qc[i] / S;
     }
 };
@@ -136,10 +131,10 @@ __device__ void first_elem(const ScanParams<P>& sp, double y, double r, ScanElem
     double Vc[P], S = r;
     for (int i = 0; i < P; i++) {
         double s = 0.0;
-        for (int k = 0; k < P; k++) s = fma(sp.V[i][k], sp.prm.c[k], s);
+        for (int k = 0; k < P; k++) s = fma(sp.V[i][k], obs_c<P>(k), s);
         Vc[i] = s;
     }
-    for (int i = 0; i < P; i++) S = fma(sp.prm.c[i], Vc[i], S);
+    for (int i = 0; i < P; i++) S = fma(obs_c<P>(i), Vc[i], S);
     for (int i = 0; i < P; i++) {
         for (int j = 0; j < P; j++) {
             e.A[i][j] = 0.0;
@@ -153,7 +148,7 @@ __device__ void first_elem(const ScanParams<P>& sp, double y, double r, ScanElem
 
 // acc <- acc (x) a_k with a_k a single-point element: Sherman-Morrison, no inverse
 template <int P>
-__device__ void fold_step(const StepOps<P>& o, const double* c, double y, ScanElem<P>& a) {
+__device__ void fold_step(const StepOps<P>& o, double y, ScanElem<P>& a) {
     double cw[P], aw[P];
     double sp_ = o.S, wb = 0.0;
     for (int i = 0; i < P; i++) {
@@ -198,7 +193,6 @@ __device__ void fold_step(const StepOps<P>& o, const double* c, double y, ScanEl
             for (int k = 0; k < P; k++) s = fma(GC[i][k], G[j][k], s);
             a.C[i][j] = s + (o.Q[i][j] - o.K[i] * o.Qc[j]);
         }
-    (void)c;
 }
 
 // Minv = (I + C J)^{-1} by Gauss-Jordan with partial pivoting; returns false if singular
@@ -335,6 +329,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_reduce_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
                    ScanElem<P>* __restrict__ E) {
     // blockIdx.y = theta row: every per-row array is offset by it
+    MathTab tb;
+    tb.load();
     spp += blockIdx.y;
     E += (size_t)blockIdx.y * nchunks;
     const int m = blockIdx.x * SCAN_BLOCK + threadIdx.x;
@@ -347,12 +343,12 @@ scan_reduce_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chu
     if (lo == 0) {
         first_elem<P>(sp, sv.y[0] - mu, scale * sv.e2_0, acc);
     } else {
-        o.build(sp, sv.dt[lo - 1], scale * sv.e2n[lo - 1]);
+        o.build(sp, tb, sv.dt[lo - 1], scale * sv.e2n[lo - 1]);
         single_elem<P>(sp, o, sv.y[lo] - mu, acc);
     }
     for (int k = lo + 1; k < hi; k++) {
-        o.build(sp, sv.dt[k - 1], scale * sv.e2n[k - 1]);
-        fold_step<P>(o, sp.prm.c, sv.y[k] - mu, acc);
+        o.build(sp, tb, sv.dt[k - 1], scale * sv.e2n[k - 1]);
+        fold_step<P>(o, sv.y[k] - mu, acc);
     }
     E[m] = acc;
 }
@@ -418,6 +414,8 @@ template <int P>
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
                    const FiltState<P>* __restrict__ F, double* __restrict__ LL) {
+    MathTab tb;
+    tb.load();
     spp += blockIdx.y;
     F += (size_t)blockIdx.y * nchunks;
     LL += (size_t)blockIdx.y * nchunks;
@@ -438,12 +436,24 @@ scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chu
 #pragma unroll
             for (int j = i; j < P; j++) kf.D[KalmanReal<P>::idx(i, j)] = f.C[i][j] - spp->V[i][j];
         }
-        kf.template predict_observe<false>(prm, sv.dt[lo - 1], sv.e2n[lo - 1]);
+        kf.template predict_observe<false>(prm, tb, sv.dt[lo - 1], sv.e2n[lo - 1]);
     }
     const int len = hi - lo;
     // every point of the chunk is scored; the transition out of the last one belongs to the next chunk
-    filter_span_impl<P, false, true>(kf, acc, prm, sv.dt + lo, sv.y + lo, sv.e2n + lo, len, len - 1);
-    LL[m] = acc.value();
+    const KalmanReal<P> kf0 = kf;
+    const SeriesPtr src{sv.dt + lo, sv.y + lo, sv.e2n + lo};
+    filter_span_impl<P, false, true>(kf, acc, prm, tb, src, len, len - 1);
+    double ll = acc.value();
+    if (acc.bad()) {  // a variance outside the normal range: redo the chunk with one log() per point
+        kf = kf0;
+        ll = 0.0;
+        for (int i = 0; i < len; i++) {
+            const double innov = (src.y[i] - prm.mu) - kf.mean;
+            ll += -0.5 * log(kf.var) - 0.5 * innov * innov / kf.var;
+            if (i + 1 < len) kf.template advance<false>(prm, tb, innov, 1.0 / kf.var, src.dt[i], src.e[i]);
+        }
+    }
+    LL[m] = ll;
 }
 
 // pass 4: deterministic fixed-order sum by one block
@@ -494,7 +504,7 @@ static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const car
     ScanElem<P>* X = (ScanElem<P>*)(base + b_sp + b_E);
     FiltState<P>* F = (FiltState<P>*)(base + b_sp + b_E + b_X);
     double* LL = (double*)(base + b_sp + b_E + b_X + b_F);
-    scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, d_theta, sp, nrows);
+    scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, sv.dt_max, d_theta, sp, nrows);
     dim3 grid((unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK), (unsigned)nrows);
     scan_reduce_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, E);
     scan_prefix_kernel<P><<<nrows, 256, 0, st>>>(sp, E, M, R, T, X, F);

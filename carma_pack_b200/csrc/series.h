@@ -33,6 +33,7 @@ struct carma_series {
     int nyp = 0;
     double* d_pack = nullptr;  // [dt | y | e2n] (3 x nyp) followed by t (ny)
     double e2_0 = 0.0;
+    double dt_max = 1.0;  // longest sampling gap
     std::vector<double> t, y, yerr;
     carma::SeriesStats st{};
     carma::DevBuf scratch_in, scratch_out, scratch_misc;
@@ -46,6 +47,7 @@ struct carma_series {
         v.e2n = d_pack + 2 * (size_t)nyp;
         v.t = d_pack + 3 * (size_t)nyp;
         v.e2_0 = e2_0;
+        v.dt_max = dt_max;
         v.ny = (int)ny;
         v.nyp = nyp;
         return v;
@@ -75,6 +77,7 @@ struct carma_multi_series {
     std::vector<carma::CurveInfo> info;  // default (population-variance) priors + statistics
     carma::DevBuf scratch_in, scratch_out, scratch_pr, scratch_misc;
     int max_ny = 0;
+    double dt_max = 1.0;  // longest sampling gap over all curves
 };
 
 namespace carma {

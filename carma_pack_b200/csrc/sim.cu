@@ -28,12 +28,14 @@ simulate_kernel(size_t ncurves, int ny, int kind, int q, int d, const double* __
                 carma_prior_t pr, double yerr, double dt_min, double dt_max, unsigned long long seed, unsigned curve_offset,
                 double* __restrict__ dt_out, double* __restrict__ y_out, double* __restrict__ e2_out,
                 CurveInfo* __restrict__ info, int* __restrict__ status) {
+    MathTab tb;
+    tb.load();
     const size_t c = (size_t)blockIdx.x * SIM_BLOCK + threadIdx.x;
     if (c >= ncurves) return;
     double th[MAX_D];
     for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? theta_true[j] : 0.0;
     RealParams<P> prm;
-    if (transform_theta<P>(kind, q, CARMA_IGNORE_BOUNDS | CARMA_LOGLIK_ONLY, pr, th, prm) != TT_OK) {
+    if (transform_theta<P>(kind, q, CARMA_IGNORE_BOUNDS | CARMA_LOGLIK_ONLY, pr, th, dt_max, prm) != TT_OK) {
         atomicExch(status, 1);
         return;
     }
@@ -68,7 +70,7 @@ simulate_kernel(size_t ncurves, int ny, int kind, int q, int d, const double* __
             dmin = fmin(dmin, dt);
             const double inv = kf.var > 0.0 ? 1.0 / kf.var : 0.0;
             kf.measurement_update(innov, inv);
-            kf.template predict_observe<false>(prm, dt, 0.0);
+            kf.template predict_observe<false>(prm, tb, dt, 0.0);
         } else {
             pdt[i] = 0.0;
         }
@@ -187,6 +189,7 @@ extern "C" int carma_multi_series_simulate(size_t ncurves, size_t ny, int kind, 
         carma_multi_series_destroy(m);
         return status ? CARMA_ERR_ARG : CARMA_ERR_CUDA;
     }
+    m->dt_max = dt_max;  // every gap is truncated at dt_max
     m->priors_pop.resize(ncurves);
     m->priors_sample.resize(ncurves);
     for (size_t c = 0; c < ncurves; c++) {

@@ -22,8 +22,11 @@
 // (The components are additionally rescaled by their MA coefficient so that c is a 0/1 row: see the
 // "real half" block at the end of transform_theta.)
 #pragma once
+#include <math.h>
+
 #include "../../include/carma_b200.h"
 #include "device_math.cuh"
+#include "fast_math.cuh"
 
 namespace carma {
 
@@ -39,27 +42,40 @@ __host__ __device__ inline int model_dim(int kind, int p, int q) {
 
 template <int P>
 struct RealParams {
-    // slot s < P/2:  conjugate pair -> lam[2s] = Re w, lam[2s+1] = Im w (of the first root, <= 0)
-    //                real pair      -> lam[2s] = w_{2s}, lam[2s+1] = w_{2s+1}
-    // odd P: lam[P-1] = w_{P-1}
-    double lam[P];
-    double c[P];  // observation row in the real basis
+    // Rates pre-multiplied by the table step of fast_math.cuh (32/ln2 for decays, 64/pi for phases):
+    //   slot s < P/2, conjugate pair w, conj(w): le[s] = Re w * 32/ln2,      ls[s] = Im w * 64/pi  (first root: Im <= 0)
+    //                 real pair w_b < w_a < 0  : le[s] = w_a * 32/ln2,       ls[s] = (w_b - w_a) * 32/ln2  (<= 0)
+    //   odd P: le[P/2] = w_{P-1} * 32/ln2
+    // Components: conjugate pair -> (Re, Im) of the MA-normalised rotated state; real pair -> (x_a + x_b, x_a - x_b);
+    // the observation is the sum of the FIRST component of every slot (+ the odd root's), for every kind of slot.
+    double le[(P + 1) / 2];
+    double ls[P / 2 > 0 ? P / 2 : 1];
     double h[P];  // stationary Cov(z, y)
     double v0;    // stationary Var(y) = Re(b V b^H)
     double scale, mu, logprior;
     unsigned cmask;  // bit s set: slot s is a conjugate pair
 };
 
+// observation row of the real basis: 1 on the first component of every 2x2 slot and on the odd root
+template <int P>
+__host__ __device__ constexpr double obs_c(int k) { return ((k & 1) == 0) ? 1.0 : 0.0; }
+
+// Largest |rate * dt| in table steps the range reductions accept: rates are clamped to it in transform_theta
+// (dt_max = the longest gap of the series).  Unreachable inside the prior (|w| <= 2 pi / dt_min) unless
+// dt_max / dt_min > 2e6; beyond it e^{w dt} differs from 0 by less than e^{-2^30 ln2/32 dt_min/dt_max}.
+constexpr double RATE_CAP_STEPS = 1073741824.0;         // 2^30: exp, k fits an int
+constexpr double PHASE_CAP_STEPS = 1125899906842624.0;  // 2^50: sin/cos, t = x + MAGIC exact
+
 enum { TT_OK = 0, TT_NEG_INF = 1 };
 
-__device__ __forceinline__ cxd cdiv_simple(cxd a, cxd b) {
+__host__ __device__ __forceinline__ cxd cdiv_simple(cxd a, cxd b) {
     double inv = 1.0 / (b.re * b.re + b.im * b.im);
     return cxd{(a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv};
 }
 
 // roots of prod_s (q1_s + q2_s x + x^2) [ * (x + q_last) ]  from log quadratic terms
 template <int N>
-__device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cxd* w) {
+__host__ __device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cxd* w) {
     unsigned cmask = 0;
 #pragma unroll
     for (int s = 0; s < N / 2; s++) {
@@ -67,7 +83,12 @@ __device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cx
             double q1 = exp(logq[2 * s]);
             double q2 = exp(logq[2 * s + 1]);
             // no FMA contraction here: the sign of the discriminant selects the branch
+#ifdef __CUDA_ARCH__
             double disc = __dsub_rn(__dmul_rn(q2, q2), __dmul_rn(4.0, q1));
+#else
+            volatile double q2q2 = q2 * q2;
+            double disc = q2q2 - 4.0 * q1;
+#endif
             if (disc > 0) {
                 double sq = sqrt(disc);
                 w[2 * s] = cx(-0.5 * (q2 + sq), 0.0);
@@ -89,7 +110,7 @@ __device__ __forceinline__ unsigned quad_roots_dev(const double* logq, int n, cx
 // (pivot = max |re|+|im|, as LAPACK izamax).  Fully unrolled, row swaps predicated, so everything
 // stays in registers.  Returns false on an exactly singular system.
 template <int P>
-__device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
+__host__ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
     cxd A[P][P];
     cxd rhs[P];
 #pragma unroll
@@ -145,7 +166,7 @@ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
 // K1 uses it: 100 registers' worth of matrix no longer compete with the 128-register cap of the kernel, so the
 // prologue stops spilling ~1 kB per thread to local memory (which reached DRAM as dead write-backs).
 template <int P>
-__device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* w, cxd* J, double* scr, int stride) {
+__host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* w, cxd* J, double* scr, int stride) {
     auto ld = [&](int i, int j) { const double* q = scr + (size_t)((i * P + j) * 2) * stride; return cxd{q[0], q[stride]}; };
     auto st = [&](int i, int j, cxd v) { double* q = scr + (size_t)((i * P + j) * 2) * stride; q[0] = v.re; q[stride] = v.im; };
     cxd rhs[P];
@@ -207,10 +228,11 @@ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* w, cxd* J
 // basis, V_r = T V T^H restricted to its real part, where z = T x.  Only the scan kernels need it.
 // lu_scratch (optional, SMEM_LU): this thread's slot of a shared-memory scratch of 2 P^2 doubles per thread,
 // laid out [element][thread] with `lu_stride` threads (see vandermonde_solve_last_smem).
+// dt_max: longest sampling gap of the series the parameters will be used on (rate clamp, see RATE_CAP_STEPS).
 template <int P, bool WITH_V = false, bool SMEM_LU = false>
-__device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr, const double* th,
-                                            RealParams<P>& out, double* Vr = nullptr, double* lu_scratch = nullptr,
-                                            int lu_stride = 0) {
+__host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr,
+                                                     const double* th, double dt_max, RealParams<P>& out,
+                                                     double* Vr = nullptr, double* lu_scratch = nullptr, int lu_stride = 0) {
     constexpr double PI = 3.14159265358979323846;
     const double ysigma = th[0], scale = th[1];
     out.scale = scale;
@@ -357,20 +379,26 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
         }
     }
     if (WITH_V) {
-        // z_m = sum_k T[m][k] x_k with at most two non-zeros per row:
-        //   conjugate pair (a, a+1): u = (x_a + x_{a+1})/2, v = (x_a - x_{a+1})/(2i); real root: z = x
+        // z_m = sum_k T[m][k] x_k with at most two non-zeros per row (x^_k = s_k x_k, s = 2b on a conjugate pair,
+        // b on a real root):
+        //   conjugate pair (a, a+1): u = (x^_a + conj-partner)/2, v = (x^_a - partner)/(2i)
+        //   real pair (a = 2s+1, b = 2s): u = x^_a + x^_b, v = x^_a - x^_b;   odd root: z = x^
         int k0[P], k1[P];
         cxd t0[P], t1[P];
 #pragma unroll
         for (int m = 0; m < P; m++) {
             int s = m >> 1;
-            bool is_c = (m < 2 * (P / 2)) && ((cmask >> s) & 1u);
+            const bool in_slot = m < 2 * (P / 2);
+            bool is_c = in_slot && ((cmask >> s) & 1u);
             if (is_c) {
-                // x^_a = s x_a, s = 2 b_a:  u^ = (s x_a + conj(s) x_a')/2,  v^ = (s x_a - conj(s) x_a')/(2i)
                 k0[m] = 2 * s; k1[m] = 2 * s + 1;
                 cxd sc = 2.0 * b[2 * s];
                 if ((m & 1) == 0) { t0[m] = 0.5 * sc; t1[m] = 0.5 * conj(sc); }
                 else { t0[m] = cx(0.0, -0.5) * sc; t1[m] = cx(0.0, 0.5) * conj(sc); }
+            } else if (in_slot) {
+                k0[m] = 2 * s + 1; k1[m] = 2 * s;
+                t0[m] = cx(b[2 * s + 1].re, 0.0);
+                t1[m] = cx(((m & 1) == 0) ? b[2 * s].re : -b[2 * s].re, 0.0);
             } else {
                 k0[m] = m; k1[m] = m; t0[m] = cx(b[m].re, 0.0); t1[m] = cx(0.0, 0.0);
             }
@@ -391,15 +419,15 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
     // ---- real half, in the observation-normalised basis.  Each rotated component is rescaled by its own
     // MA coefficient, x^_k = s_k x_k with s = 2 b (conjugate pair) or b (real root); the scaling commutes
     // with the diagonal transition, and the observation becomes y = sum of the FIRST component of every
-    // slot (+ both components of a real pair): the row c only holds 0/1 and the time loop needs no
-    // multiplications by b.
+    // slot: a real pair is carried as (x^_a + x^_b, x^_a - x^_b), a = the root closer to zero, so its
+    // transition e^{w_a dt} [[ch, sh], [sh, ch]] has the shape of a rotation (fast_math.cuh) and the time
+    // loop needs neither multiplications by b nor a per-lane observation row.
+    const double rate_cap = RATE_CAP_STEPS / dt_max, phase_cap = PHASE_CAP_STEPS / dt_max;
 #pragma unroll
     for (int s = 0; s < P / 2; s++) {
         if ((cmask >> s) & 1u) {
-            out.lam[2 * s] = w[2 * s].re;
-            out.lam[2 * s + 1] = w[2 * s].im;
-            out.c[2 * s] = 1.0;
-            out.c[2 * s + 1] = 0.0;
+            out.le[s] = fmax(w[2 * s].re * K_EXP_SCALE, -rate_cap);
+            out.ls[s] = fmax(w[2 * s].im * K_ROT_SCALE, -phase_cap);
             // h restricted to the conjugate-symmetric subspace: (h_{2s} + conj(h_{2s+1})) / 2.  The LU
             // solution J is not exactly conjugate-symmetric (its error is cond(E) eps, consistent across
             // components); averaging keeps c.h == Re(b V b^H) to rounding, which is what the reference's
@@ -410,19 +438,19 @@ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, con
             out.h[2 * s] = hh.re;
             out.h[2 * s + 1] = hh.im;
         } else {
-            out.lam[2 * s] = w[2 * s].re;
-            out.lam[2 * s + 1] = w[2 * s + 1].re;
-            out.c[2 * s] = 1.0;
-            out.c[2 * s + 1] = 1.0;
-            out.h[2 * s] = b[2 * s].re * h[2 * s].re;
-            out.h[2 * s + 1] = b[2 * s + 1].re * h[2 * s + 1].re;
+            // ARRoots order: w[2s] = -(q2 + sqrt(disc))/2 < w[2s+1] = -(q2 - sqrt(disc))/2 < 0
+            out.le[s] = fmax(w[2 * s + 1].re * K_EXP_SCALE, -rate_cap);
+            out.ls[s] = fmax((w[2 * s].re - w[2 * s + 1].re) * K_EXP_SCALE, -rate_cap);
+            const double ha = b[2 * s + 1].re * h[2 * s + 1].re, hb = b[2 * s].re * h[2 * s].re;
+            out.h[2 * s] = ha + hb;
+            out.h[2 * s + 1] = ha - hb;
         }
     }
     if (P & 1) {
-        out.lam[P - 1] = w[P - 1].re;
-        out.c[P - 1] = 1.0;
+        out.le[P / 2] = fmax(w[P - 1].re * K_EXP_SCALE, -rate_cap);
         out.h[P - 1] = b[P - 1].re * h[P - 1].re;
     }
+    if (P < 2) out.ls[0] = 0.0;
 
     // ---- log prior (carpack.hpp:118-126, 444-456)
     double lp = 0.0;

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CARMA_B200_ABI_VERSION 2
+#define CARMA_B200_ABI_VERSION 3
 
 enum {
     CARMA_OK = 0,
@@ -263,9 +263,15 @@ int carma_fp64_peak_tflops(int device, double* tflops);
 int carma_philox_dev(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t seed, uint32_t* out4);
 int carma_tdist_dev(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, int dof, double* out);
 
-/* The branch-free exp / sincos / reciprocal used inside the Kalman time loop (csrc/fast_math.cuh),
- * evaluated element-wise on host arrays, so tests can bound their error against libm. */
-int carma_fastmath_dev(const double* x, size_t n, double* out_exp, double* out_sin, double* out_cos, double* out_rcp);
+/* The branch-free transcendentals of the Kalman time loop (csrc/fast_math.cuh), evaluated element-wise on host
+ * arrays so tests can bound their error against libm.  rate is in TABLE STEPS per unit time, as the loop holds it
+ * (lambda * 32/ln2 for a decay, Im(omega) * 64/pi for a phase):
+ *   out_exp      = exp(rate dt ln2/32)                        (rate <= 0)
+ *   out_sin/cos  = sin, cos(rate dt pi/64)                    (NaN if the all-conjugate and generic variants differ)
+ *   out_sh/ch    = (1 - rho)/2, (1 + rho)/2, rho = out_exp    (transition of a real root pair)
+ *   out_rcp      = 1 / rate */
+int carma_fastmath_dev(const double* rate, const double* dt, size_t n, double* out_exp, double* out_sin, double* out_cos,
+                       double* out_sh, double* out_ch, double* out_rcp);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -18,6 +20,22 @@ def pytest_configure(config):
     if not os.path.exists(os.path.join(ROOT, "carma_pack_b200", "libcarma_b200.so")):
         import build_native
         build_native.build_all(force=False)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Audit trail of the noise-floor criterion (tests/parity_util.py): printed even under -q."""
+    import parity_util
+    rep = parity_util.write_report(ROOT)
+    if not rep:
+        return
+    tr = terminalreporter
+    tr.write_line("")
+    tr.write_line("log-density parity audit (rtol %.0e; rows that needed the oracle-noise-floor criterion):" % rep["rtol"])
+    for r in rep["calls"]:
+        tr.write_line("  %-46s rows %7d  noise-floor rows %5d (%.4f%%, allowed %.3g%%)  worst err/noise %.2f  max rel err elsewhere %.2e"
+                      % (r["what"][:46], r["rows"], r["noise_floor_rows"], 100 * r["noise_floor_frac"], 100 * r["allowed_frac"],
+                         r["worst_err_over_noise"], r["max_rel_err_other_rows"]))
+    tr.write_line("  total: %d of %d rows" % (rep["total_noise_floor_rows"], rep["total_rows"]))
 
 
 @pytest.fixture(scope="session")

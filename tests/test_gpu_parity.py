@@ -11,10 +11,10 @@ import numpy as np
 import pytest
 
 from conftest import golden_case_names
+from parity_util import RTOL, assert_logpost_parity, ulp_shift
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-9
 
 
 @pytest.fixture(scope="module")
@@ -33,49 +33,6 @@ def O():
 
 def to_prior(C, opr):
     return C.Prior(opr.max_stdev, opr.max_freq, opr.min_freq, opr.kappa_low, opr.kappa_high, opr.measerr_dof)
-
-
-def assert_logpost_parity(got, want, want_ld=None, rtol=RTOL, max_illcond_frac=0.002, what="", ulp_eval=None):
-    """got vs want at rtol.  Rows that miss rtol are accepted only if the REFERENCE algorithm is itself
-    not reproducible to rtol there, measured two ways: (a) |double - long double| of the oracle, and
-    (b) `ulp_eval(rows, k)` = the oracle re-evaluated with every theta component moved by k ulps
-    (the device exp() legitimately differs from glibc's by an ulp, which moves near-degenerate roots).
-    Such rows are counted and must stay below max_illcond_frac."""
-    got, want = np.asarray(got), np.asarray(want)
-    fin_w, fin_g = np.isfinite(want), np.isfinite(got)
-    # same class: finite / -inf / nan
-    assert np.array_equal(fin_w, fin_g), "%s: finite-class mismatch at %s" % (what, np.where(fin_w != fin_g)[0][:10])
-    ninf_w, ninf_g = want == -np.inf, got == -np.inf
-    assert np.array_equal(ninf_w, ninf_g), "%s: -inf class mismatch" % what
-    idx = np.nonzero(fin_w)[0]
-    err = np.abs(got[fin_w] - want[fin_w])
-    tol = rtol * np.maximum(np.abs(want[fin_w]), 1.0)
-    bad = err > tol
-    if want_ld is None:
-        assert not bad.any(), "%s: max rel err %.3e" % (what, np.max(err / np.maximum(np.abs(want[fin_w]), 1.0)))
-        return 0
-    noise = np.abs(np.asarray(want_ld)[fin_w] - want[fin_w])
-    if ulp_eval is not None and bad.any():
-        rows = idx[bad]
-        for k in (1, -1, 2, -2):
-            pert = ulp_eval(rows, k)
-            dlt = np.abs(pert - want[rows])
-            noise[bad] = np.maximum(noise[bad], np.where(np.isfinite(dlt), dlt, np.inf))
-    really_bad = bad & (err > 50.0 * noise + tol)
-    assert not really_bad.any(), "%s: %d rows differ beyond tolerance and beyond the oracle's own noise floor: %s" % (
-        what, really_bad.sum(), idx[really_bad][:10])
-    assert bad.mean() <= max_illcond_frac, "%s: %.4f of rows needed the noise-floor criterion" % (what, bad.mean())
-    return int(bad.sum())
-
-
-def ulp_shift(theta, k):
-    """Move every component k ulps (alternating direction by column so the perturbation is generic)."""
-    th = np.array(theta, dtype=np.float64)
-    sign = np.where(np.arange(th.shape[1]) % 2 == 0, 1.0, -1.0) * np.sign(k)
-    out = th.copy()
-    for _ in range(abs(k)):
-        out = np.nextafter(out, out + sign[None, :] * np.inf)
-    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -421,22 +378,33 @@ def test_scan_kalman_matches_sequential_and_oracle(C, O):
 
 
 def test_fast_math_accuracy(C):
-    """exp_fast / sincos_fast / rcp_fast (csrc/fast_math.cuh) against numpy in long double."""
+    """exp_scaled / rot_scaled / rcp_fast (csrc/fast_math.cuh) on the device against long double / exact rational
+    argument reduction: the error budget of one transition factor of the time loop."""
+    from fractions import Fraction
     rng = np.random.default_rng(0)
-    x = np.concatenate([-np.exp(rng.uniform(np.log(1e-8), np.log(700.0), 20000)),
-                        [0.0, -1e-300, -707.9, -708.1, -745.0, -1e4, -1e14, -1e300], rng.uniform(-1.0, 1.0, 2000)])
-    e, _, _, _ = C._lib.fastmath_dev(x)
-    want = np.exp(x.astype(np.longdouble))
-    big = x >= -708.0
-    rel = np.abs(e[big] - want[big]) / want[big]
+    n = 40000
+    lnat = -np.exp(rng.uniform(np.log(1e-6), np.log(50.0), n))
+    dt = np.exp(rng.uniform(np.log(1e-2), np.log(30.0), n))
+    l_exp = lnat * (32.0 / np.log(2.0))
+    ex, _, _, s_r, c_r, _ = C._lib.fastmath_dev(l_exp, dt)
+    x = l_exp.astype(np.longdouble) * dt.astype(np.longdouble) * (np.log(np.longdouble(2)) / 32)
+    want = np.exp(x)
+    ok = x > -700
+    rel = np.abs(ex[ok] - want[ok]) / want[ok]
     assert rel.max() < 4e-16, rel.max()
-    assert np.all(e[~big] == 0.0)   # flushed below exp(-708), including arguments far outside the reduction range
-    xs = np.concatenate([rng.uniform(-1e5, 1e5, 20000), rng.uniform(-10, 10, 5000), [0.0, 1e9, -3.3e12]])
-    _, s, c, _ = C._lib.fastmath_dev(xs)
-    ws, wc = np.sin(xs.astype(np.longdouble)), np.cos(xs.astype(np.longdouble))
-    assert np.abs(s - ws).max() < 4e-16 and np.abs(c - wc).max() < 4e-16
+    assert np.all(ex[~ok] < 1e-300) and np.all(ex >= 0)   # clamped exponent instead of a flush branch
+    assert np.abs(c_r - (1 + want) / 2).max() < 3e-16 and np.abs(s_r - (1 - want) / 2).max() < 3e-16
+    lp = -np.exp(rng.uniform(np.log(1e-3), np.log(1e7), n))
+    _, s_c, c_c, _, _, rc = C._lib.fastmath_dev(lp, dt)
+    assert not np.isnan(s_c).any()   # NaN marks a bit difference between the all-conjugate and the generic variant
+    pick = rng.choice(n, 3000, replace=False)
+    red = np.array([float(((Fraction(float(lp[i])) * Fraction(float(dt[i]))) % 128)) for i in pick], dtype=np.longdouble)
+    lo = np.array([float((Fraction(float(lp[i])) * Fraction(float(dt[i]))) % 128 - Fraction(float(red[k]))) for k, i in enumerate(pick)],
+                  dtype=np.longdouble)
+    ang = (red + lo) * np.longdouble(np.pi) / 64 + (red + lo) * np.longdouble(1.2246467991473532e-16) / 64
+    assert np.abs(s_c[pick] - np.sin(ang)).max() < 4e-16 and np.abs(c_c[pick] - np.cos(ang)).max() < 4e-16
     xr = np.concatenate([np.exp(rng.uniform(np.log(1e-200), np.log(1e200), 20000)), -np.exp(rng.uniform(-5, 5, 100))])
-    _, _, _, r = C._lib.fastmath_dev(xr)
+    r = C._lib.fastmath_dev(xr, np.ones_like(xr))[5]
     assert (np.abs(r * xr - 1.0)).max() < 5e-16
 
 

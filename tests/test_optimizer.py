@@ -135,3 +135,45 @@ def test_native_lbfgs_core_matches_twin_on_car_loglik():
     assert np.isfinite(fa).all()
     assert abs(fa.min() - fb.min()) < 1e-4 * max(1.0, abs(fb.min()))
     assert np.mean(np.abs(fa - fb) < 1e-2 * np.maximum(1.0, np.abs(fb))) >= 0.75
+
+
+def test_rows_do_not_depend_on_their_batch_mates():
+    """Every start keeps its own L-BFGS history: a row whose (s, y) pair fails the curvature test must not be
+    handed a zero pair because some OTHER row passed it (that collapsed H0 to 1e-8 I and froze the row far from a
+    stationary point).  Non-convex objective with negative curvature near the origin; the result of a row is the
+    same whether it runs alone or next to other starts -- in the numpy twin and in the native core."""
+    def f(z):
+        return np.sum(z ** 4 - z ** 2 + 0.1 * z, axis=1)
+
+    lo = np.full(2, -10.0)
+    hi = np.full(2, 10.0)
+    a = np.array([[0.05, 0.02]])
+    both = np.array([[0.05, 0.02], [2.0, 3.0]])
+    fmin = 2 * min(v ** 4 - v ** 2 + 0.1 * v for v in np.linspace(-1.5, 1.5, 300001))
+    for opt in (batched_lbfgs, _native()):
+        xs, fs, _, _ = opt(f, a, lo, hi, maxiter=200)
+        xb, fb, _, _ = opt(f, both, lo, hi, maxiter=200)
+        assert np.array_equal(xs[0], xb[0]) and fs[0] == fb[0], (opt, xs, xb)
+        assert fb[0] < -0.5, fb                     # a genuine local minimum, not the stall at f = -0.003
+        assert fb.min() <= fmin + 1e-6 or fb[0] <= fmin + 0.15, (fb, fmin)
+        # order inside the batch is irrelevant too
+        xr, fr, _, _ = opt(f, both[::-1].copy(), lo, hi, maxiter=200)
+        assert np.array_equal(xr[::-1], xb) and np.array_equal(fr[::-1], fb)
+
+
+def test_gradient_next_to_an_infeasible_region_uses_the_other_side():
+    """A forward-difference point without a finite value is retried with a backward difference, so a start that
+    sits next to the edge of the support is not reported as stationary there."""
+    def f(z):
+        v = (z[:, 0] + 3.0) ** 2 + (z[:, 1] + 1.0) ** 2
+        v[z[:, 0] > 1.0] = np.inf           # the density has no support beyond x0 = 1
+        return v
+
+    lo = np.full(2, -50.0)
+    hi = np.full(2, 50.0)
+    x0 = np.array([[1.0, 4.0], [1.0 - 5e-9, -3.0]])   # forward step (+1e-8) leaves the support for both rows
+    for opt in (batched_lbfgs, _native()):
+        x, fv, _, _ = opt(f, x0, lo, hi, maxiter=100)
+        # with the component zeroed (old behaviour) x0 would have stayed at 1 and f at 16
+        assert np.allclose(x, [[-3.0, -1.0]] * 2, atol=1e-4), (opt, x)
+        assert np.all(fv < 1e-7), (opt, fv)
