@@ -68,8 +68,42 @@ constexpr double PHASE_CAP_STEPS = 1125899906842624.0;  // 2^50: sin/cos, t = x 
 
 enum { TT_OK = 0, TT_NEG_INF = 1 };
 
+// ---- divisions of the prologue.  An IEEE FP64 division costs ~14 issued instructions on sm_100a (reciprocal seed,
+// Newton steps, range check, a branch around the slow-path call) and splits the basic block; the round-1 prologue
+// executed ~170 of them per theta and was 17-19 % of K1 at ny = 270.  Here: one branch-free reciprocal-multiply with
+// a residual correction (error < 1 ulp; operands are normal numbers for every theta the prior admits -- a
+// denominator outside the normal range yields a non-finite result, which transform_theta catches at its end and
+// redoes with IEEE divisions), complex divisions as ONE complex reciprocal times a complex product (what LAPACK's
+// zgetf2 does with the pivots: it scales the column by 1/pivot), and no division at all in the prior-bound tests
+// unless a value falls within 1e-12 relative of its bound.
+template <bool FAST>
+__host__ __device__ __forceinline__ double div_(double a, double b) {
+    if (!FAST) return a / b;
+    const double r = rcp_fast(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+// 1 / b, Smith's scaling (robust against overflow of |b|^2)
+template <bool FAST>
+__host__ __device__ __forceinline__ cxd crcp(cxd b) {
+    if (fabs(b.re) >= fabs(b.im)) {
+        const double r = div_<FAST>(b.im, b.re), den = fma(b.im, r, b.re);
+        const double id = div_<FAST>(1.0, den);
+        return cxd{id, -r * id};
+    } else {
+        const double r = div_<FAST>(b.re, b.im), den = fma(b.re, r, b.im);
+        const double id = div_<FAST>(1.0, den);
+        return cxd{r * id, -id};
+    }
+}
+template <bool FAST>
+__host__ __device__ __forceinline__ cxd cdiv_(cxd a, cxd b) {
+    if (!FAST) return cdiv(a, b);
+    return a * crcp<true>(b);
+}
+template <bool FAST>
 __host__ __device__ __forceinline__ cxd cdiv_simple(cxd a, cxd b) {
-    double inv = 1.0 / (b.re * b.re + b.im * b.im);
+    double inv = div_<FAST>(1.0, b.re * b.re + b.im * b.im);
     return cxd{(a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv};
 }
 
@@ -109,10 +143,10 @@ __host__ __device__ __forceinline__ unsigned quad_roots_dev(const double* logq, 
 // Solve E J = e_{P-1} with E(i,k) = w_k^i (kfilter.cpp:144-158) by LU with partial pivoting
 // (pivot = max |re|+|im|, as LAPACK izamax).  Fully unrolled, row swaps predicated, so everything
 // stays in registers.  Returns false on an exactly singular system.
-template <int P>
+template <int P, bool FAST>
 __host__ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cxd* J) {
     cxd A[P][P];
-    cxd rhs[P];
+    cxd rhs[P], pinv[P];
 #pragma unroll
     for (int k = 0; k < P; k++) {
         cxd pw = cx(1, 0);
@@ -143,9 +177,10 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cx
                 cxd tr = rhs[k]; rhs[k] = rhs[i]; rhs[i] = tr;
             }
         }
+        pinv[k] = crcp<FAST>(A[k][k]);  // one reciprocal per pivot: column scaled by it, reused in the back-substitution
 #pragma unroll
         for (int i = k + 1; i < P; i++) {
-            cxd l = cdiv(A[i][k], A[k][k]);
+            cxd l = FAST ? A[i][k] * pinv[k] : cdiv(A[i][k], A[k][k]);
 #pragma unroll
             for (int j = k + 1; j < P; j++) A[i][j] = A[i][j] - l * A[k][j];
             rhs[i] = rhs[i] - l * rhs[k];
@@ -156,7 +191,7 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cx
         cxd s = rhs[i];
 #pragma unroll
         for (int j = i + 1; j < P; j++) s = s - A[i][j] * J[j];
-        J[i] = cdiv(s, A[i][i]);
+        J[i] = FAST ? s * pinv[i] : cdiv(s, A[i][i]);
     }
     return ok;
 }
@@ -165,11 +200,11 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last(const cxd* w, cx
 // memory instead of registers: element (i,j) of the calling thread is scr[((i*P + j)*2 + {0,1}) * stride].
 // K1 uses it: 100 registers' worth of matrix no longer compete with the 128-register cap of the kernel, so the
 // prologue stops spilling ~1 kB per thread to local memory (which reached DRAM as dead write-backs).
-template <int P>
+template <int P, bool FAST>
 __host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* w, cxd* J, double* scr, int stride) {
     auto ld = [&](int i, int j) { const double* q = scr + (size_t)((i * P + j) * 2) * stride; return cxd{q[0], q[stride]}; };
     auto st = [&](int i, int j, cxd v) { double* q = scr + (size_t)((i * P + j) * 2) * stride; q[0] = v.re; q[stride] = v.im; };
-    cxd rhs[P];
+    cxd rhs[P], pinv[P];
 #pragma unroll
     for (int k = 0; k < P; k++) {
         cxd pw = cx(1, 0);
@@ -203,11 +238,15 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* 
             if (i == piv) { cxd tr = rhs[k]; rhs[k] = rhs[i]; rhs[i] = tr; }
         }
         akk = ld(k, k);
+        pinv[k] = crcp<FAST>(akk);
+        cxd rowk[P];  // row k of the active block stays in registers for the whole column
+#pragma unroll
+        for (int j = k + 1; j < P; j++) rowk[j] = ld(k, j);
 #pragma unroll
         for (int i = k + 1; i < P; i++) {
-            cxd l = cdiv(ld(i, k), akk);
+            cxd l = FAST ? ld(i, k) * pinv[k] : cdiv(ld(i, k), akk);
 #pragma unroll
-            for (int j = k + 1; j < P; j++) st(i, j, ld(i, j) - l * ld(k, j));
+            for (int j = k + 1; j < P; j++) st(i, j, ld(i, j) - l * rowk[j]);
             rhs[i] = rhs[i] - l * rhs[k];
         }
     }
@@ -216,7 +255,7 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* 
         cxd s = rhs[i];
 #pragma unroll
         for (int j = i + 1; j < P; j++) s = s - ld(i, j) * J[j];
-        J[i] = cdiv(s, ld(i, i));
+        J[i] = FAST ? s * pinv[i] : cdiv(s, ld(i, i));
     }
     return ok;
 }
@@ -229,10 +268,12 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* 
 // lu_scratch (optional, SMEM_LU): this thread's slot of a shared-memory scratch of 2 P^2 doubles per thread,
 // laid out [element][thread] with `lu_stride` threads (see vandermonde_solve_last_smem).
 // dt_max: longest sampling gap of the series the parameters will be used on (rate clamp, see RATE_CAP_STEPS).
-template <int P, bool WITH_V = false, bool SMEM_LU = false>
-__host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr,
-                                                     const double* th, double dt_max, RealParams<P>& out,
-                                                     double* Vr = nullptr, double* lu_scratch = nullptr, int lu_stride = 0) {
+// FAST: the reciprocal-multiply divisions above (hot path); !FAST: IEEE divisions (reached only when the fast
+// evaluation produced a non-finite constant, i.e. some denominator left the normal range).
+template <int P, bool WITH_V, bool SMEM_LU, bool FAST>
+__host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsigned flags, const carma_prior_t& pr,
+                                                          const double* th, double dt_max, RealParams<P>& out, double* Vr,
+                                                          double* lu_scratch, int lu_stride) {
     constexpr double PI = 3.14159265358979323846;
     const double ysigma = th[0], scale = th[1];
     out.scale = scale;
@@ -256,26 +297,63 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
             return TT_NEG_INF;
     } else if (!(flags & CARMA_IGNORE_BOUNDS)) {
         bool ok = true;
-        double prev_cent = 0.0;
-#pragma unroll
-        for (int i = 0; i < P; i++) {
-            double cent = fabs(w[i].im) / 2.0 / PI;
-            double width = -w[i].re / 2.0 / PI;
-            ok = ok && (cent < pr.max_freq) && (width < pr.max_freq) && (width > pr.min_freq);
-            if (i > 0 && (cent - prev_cent > 1e-8)) ok = false;
-            prev_cent = cent;
-        }
         if ((ysigma > pr.max_stdev) || (ysigma < 0) || (scale < 0.5) || (scale > 2.0)) ok = false;
-        // unique_roots(ar_roots, 1e-4): carpack.cpp:709-732
-        double min_frac = 100.0 * 1e-4;
+        // centroid / width bounds and ordering (carpack.cpp:318-352): x / 2 / pi against a bound.  The product
+        // x * (1/2pi) is within 2 ulp of that quotient; only a comparison closer than 1e-12 relative to its
+        // threshold is redone with the reference's divisions.
+        // unique_roots(ar_roots, 1e-4) (carpack.cpp:709-732): |(w_i - w_j) / (w_i + w_j)| > 1e-4 for every pair, decided
+        // on the squared moduli unless the ratio is within 1e-9 of the threshold.
+        bool unsure = false;
+        if (FAST) {
+            constexpr double INV2PI = 0.15915494309189533576888;
+            constexpr double G = 1e-12;
+            double prev_cent = 0.0;
 #pragma unroll
-        for (int i = 0; i < P - 1; i++)
-#pragma unroll
-            for (int j = i + 1; j < P; j++) {
-                double frac = cabs_(cdiv(w[i] - w[j], w[i] + w[j]));
-                if (frac < min_frac) min_frac = frac;
+            for (int i = 0; i < P; i++) {
+                const double cent = fabs(w[i].im) * INV2PI, width = -w[i].re * INV2PI;
+                ok = ok && (cent < pr.max_freq) && (width < pr.max_freq) && (width > pr.min_freq);
+                unsure = unsure || (fabs(cent - pr.max_freq) <= G * pr.max_freq) || (fabs(width - pr.max_freq) <= G * pr.max_freq) ||
+                         (fabs(width - pr.min_freq) <= G * pr.min_freq);
+                if (i > 0) {
+                    const double gap = cent - prev_cent;
+                    if (gap > 1e-8) ok = false;
+                    unsure = unsure || (fabs(gap - 1e-8) <= G * fmax(cent, prev_cent));
+                }
+                prev_cent = cent;
             }
-        if (!(min_frac > 1e-4)) ok = false;
+#pragma unroll
+            for (int i = 0; i < P - 1; i++)
+#pragma unroll
+                for (int j = i + 1; j < P; j++) {
+                    const cxd dmn = w[i] - w[j], sm = w[i] + w[j];
+                    const double n2 = dmn.re * dmn.re + dmn.im * dmn.im, d2 = sm.re * sm.re + sm.im * sm.im;
+                    if (!(n2 > 1.000000001e-8 * d2)) {
+                        if (n2 < 0.999999999e-8 * d2) ok = false;
+                        else unsure = true;  // also NaN / overflowed squares
+                    }
+                }
+        }
+        if (!FAST || unsure) {
+            ok = !((ysigma > pr.max_stdev) || (ysigma < 0) || (scale < 0.5) || (scale > 2.0));
+            double prev_cent = 0.0;
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                double cent = fabs(w[i].im) / 2.0 / PI;
+                double width = -w[i].re / 2.0 / PI;
+                ok = ok && (cent < pr.max_freq) && (width < pr.max_freq) && (width > pr.min_freq);
+                if (i > 0 && (cent - prev_cent > 1e-8)) ok = false;
+                prev_cent = cent;
+            }
+            double min_frac = 100.0 * 1e-4;
+#pragma unroll
+            for (int i = 0; i < P - 1; i++)
+#pragma unroll
+                for (int j = i + 1; j < P; j++) {
+                    double frac = cabs_(cdiv(w[i] - w[j], w[i] + w[j]));
+                    if (frac < min_frac) min_frac = frac;
+                }
+            if (!(min_frac > 1e-4)) ok = false;
+        }
         if (!ok) return TT_NEG_INF;
     }
 
@@ -302,7 +380,7 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
             const double norm = ld(q).re;
 #pragma unroll
             for (int i = 0; i < P; i++)
-                if (i <= q) ma[i] = ld(q - i).re / norm;
+                if (i <= q) ma[i] = div_<FAST>(ld(q - i).re, norm);
         } else {
             cxd cf[P];
 #pragma unroll
@@ -311,7 +389,7 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
             for (int i = 0; i < q; i++)
                 for (int j = i + 1; j >= 1; j--) cf[j] = cf[j] - r[i] * cf[j - 1];
             double norm = cf[q].re;
-            for (int i = 0; i <= q; i++) ma[i] = cf[q - i].re / norm;
+            for (int i = 0; i <= q; i++) ma[i] = div_<FAST>(cf[q - i].re, norm);
         }
     } else if (kind == CARMA_KIND_ZCARMA) {
         double x = th[3 + P];
@@ -343,13 +421,13 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
         for (int l = 0; l < P; l++)
             if (l != k) dp = dp * ((w[l] - w[k]) * (conj(w[l]) + w[k]));
         cxd denom = (-2.0 * w[k].re) * dp;
-        var_acc = var_acc + cdiv(s1 * s2, denom);
+        var_acc = var_acc + cdiv_<FAST>(s1 * s2, denom);
     }
     double sigsqr;
     if (kind == CARMA_KIND_CAR1)
         sigsqr = 2.0 * ysigma * ysigma * (-w[0].re);  // carpack.hpp:272-274
     else
-        sigsqr = ysigma * ysigma / var_acc.re;  // carpack.hpp:316-319, 391-395
+        sigsqr = div_<FAST>(ysigma * ysigma, var_acc.re);  // carpack.hpp:316-319, 391-395
 
     // ---- J = E^{-1} e_p for the Vandermonde E (kfilter.cpp:144-158): LU with partial pivoting, as
     // arma::solve -> zgesv does.  (The closed form J_k = 1/prod_{l!=k}(w_k - w_l) has a smaller forward
@@ -358,8 +436,8 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
     // roots is benign under such consistent perturbations while it amplifies independent ones.)
     cxd J[P];
     bool solved;
-    if (SMEM_LU) solved = vandermonde_solve_last_smem<P>(w, J, lu_scratch, lu_stride);
-    else solved = vandermonde_solve_last<P>(w, J);
+    if (SMEM_LU) solved = vandermonde_solve_last_smem<P, FAST>(w, J, lu_scratch, lu_stride);
+    else solved = vandermonde_solve_last<P, FAST>(w, J);
     if (!solved) return TT_NEG_INF;  // arma::solve throws -> -inf (carpack.hpp:154-164)
 
     // ---- stationary covariance V (kfilter.cpp:165-172), h = V b^H, v0 = Re(b V b^H)
@@ -372,7 +450,7 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
 #pragma unroll
         for (int j = i; j < P; j++) {
             cxd num = (-sigsqr) * (J[i] * conj(J[j]));
-            cxd vij = cdiv_simple(num, w[i] + conj(w[j]));
+            cxd vij = cdiv_simple<FAST>(num, w[i] + conj(w[j]));
             h[i] = h[i] + vij * conj(b[j]);
             if (j > i) h[j] = h[j] + conj(vij) * conj(b[i]);
             if (WITH_V) { Vfull[i][j] = vij; Vfull[j][i] = conj(vij); }
@@ -463,6 +541,22 @@ __host__ __device__ __noinline__ int transform_theta(int kind, int q, unsigned f
     }
     out.logprior = lp;
     return TT_OK;
+}
+
+template <int P, bool WITH_V = false, bool SMEM_LU = false>
+__host__ __device__ __forceinline__ int transform_theta(int kind, int q, unsigned flags, const carma_prior_t& pr,
+                                                        const double* th, double dt_max, RealParams<P>& out,
+                                                        double* Vr = nullptr, double* lu_scratch = nullptr, int lu_stride = 0) {
+    int st = transform_theta_impl<P, WITH_V, SMEM_LU, true>(kind, q, flags, pr, th, dt_max, out, Vr, lu_scratch, lu_stride);
+    if (st == TT_OK) {
+        // every constant of the recursion must be finite; otherwise a denominator left the range of the fast
+        // reciprocal (or theta itself is absurd): let the IEEE-division version decide
+        double chk = out.v0;
+#pragma unroll
+        for (int i = 0; i < P; i++) chk += out.h[i];
+        if (!isfinite(chk)) st = transform_theta_impl<P, WITH_V, SMEM_LU, false>(kind, q, flags, pr, th, dt_max, out, Vr, lu_scratch, lu_stride);
+    }
+    return st;
 }
 
 }  // namespace carma
