@@ -41,11 +41,27 @@ def f_eval(p, ny):
     return (ny - 1) * f_step(p) + f_reset
 
 
+def load_synth():
+    """carma_pack_b200/synth.py (numpy only) loaded BY PATH: the reference arm must not import the product
+    package (importing it loads libcarma_b200.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_synth", os.path.join(ROOT, "carma_pack_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_inputs(seed_offset=0):
-    from carma_pack_b200 import synth
+    synth = load_synth()
     t, y, e = synth.readme_series(NY, 270)
     th = synth.theta_batch(NTHETA, t, y, p=P, q=Q, seed=1000 + seed_offset)
     return t, y, e, th
+
+
+def workload_config():
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": "batched log-likelihood: 65,536 CARMA(5,3) parameter vectors on one ny=270 series per GPU "
+                        "(BASELINE config 2)", "p": P, "q": Q, "ny": NY, "thetas_per_step": NTHETA}
 
 
 class ClockSampler(threading.Thread):
@@ -87,25 +103,26 @@ class ClockSampler(threading.Thread):
 
 def _oracle_worker(args):
     from oracle import oracle as O
-    t, y, e, th = args
+    t, y, e, th, lean = args
     pr = O.default_prior(t, y)
-    return O.logdensity(O.KIND_CARMA, P, Q, t, y, e, th, prior=pr, fast=True)
+    return O.logdensity(O.KIND_CARMA, P, Q, t, y, e, th, prior=pr, fast=True, lean=lean)
 
 
-def cpu_oracle_rate(t, y, e, th, cores):
-    """evals/s of the CPU oracle (oracle/carma_oracle.cpp, -O3 x86-64-v3) on `cores` processes."""
+def cpu_oracle_rate(t, y, e, th, cores, lean=False):
+    """evals/s of the CPU oracle (oracle/carma_oracle.cpp, -O3 x86-64-v3) on `cores` processes.
+    lean: the fixed-size heap-free variant instead of the dense as-written one."""
     from oracle import oracle as O
     O.build()
     if cores == 1:
         t0 = time.perf_counter()
-        _oracle_worker((t, y, e, th))
+        _oracle_worker((t, y, e, th, lean))
         return th.shape[0] / (time.perf_counter() - t0)
     import multiprocessing as mp
     chunks = np.array_split(th, cores)
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_oracle_worker, [(t, y, e, c[:64]) for c in chunks])  # warm the pool
+        pool.map(_oracle_worker, [(t, y, e, c[:64], lean) for c in chunks])  # warm the pool
         t0 = time.perf_counter()
-        pool.map(_oracle_worker, [(t, y, e, c) for c in chunks])
+        pool.map(_oracle_worker, [(t, y, e, c, lean) for c in chunks])
         dt = time.perf_counter() - t0
     return th.shape[0] / dt
 
@@ -124,13 +141,16 @@ def run_reference(args, rank, world):
     rates = [cpu_oracle_rate(t, y, e, sample, cores) for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     value = float(np.mean(rates))
+    lean = float(cpu_oracle_rate(t, y, e, sample, cores, lean=True))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched log-likelihood: CARMA(5,3) parameter vectors on one ny=270 series "
-                               "(BASELINE config 2)", "p": P, "q": Q, "ny": NY, "thetas_per_step": int(sample.shape[0])},
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "variant": "dense as-written (per-call vector copies, full p x p complex products)",
+                         "lean_variant_value": lean,
+                         "lean_variant": "same arithmetic, fixed-size arrays, no heap in the time loop (bitwise equal results)",
                          "sample": "%d of the 65,536 theta rows per step, split over %d processes" % (sample.shape[0], cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -255,14 +275,17 @@ def run_ours(args, rank, world, local_rank):
         C._lib.check(lib.carma_loglik_batch(series.handle, C.KIND_CARMA, P, Q, ctypes.byref(prior), NTHETA,
                                             h_theta[0].data_ptr(), h_out.data_ptr(), 0), "carma_loglik_batch")
 
+    E2E_REPEATS = 5   # the K-step region lasts a few ms: repeat it and report the median (max over ranks per repeat)
     for _ in range(3):
         e2e_step()
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_step()  # synchronous: returns after the D2H copy completed
-    e2e_block_s = time.perf_counter() - t0
+    block_s = []
+    for _ in range(E2E_REPEATS):
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()  # synchronous: returns after the D2H copy completed
+        block_s.append(time.perf_counter() - t0)
 
     def e2e_pipelined(nsteps):
         for k in range(nsteps):
@@ -274,15 +297,18 @@ def run_ours(args, rank, world, local_rank):
         series.loglik_wait(1)
 
     e2e_pipelined(4)
+    pipe_s = []
+    for _ in range(E2E_REPEATS):
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined(K)
+        pipe_s.append(time.perf_counter() - t0)
     if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    e2e_pipelined(K)
-    e2e_s = time.perf_counter() - t0
-    if dist:
-        tt = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor(pipe_s + block_s, dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_block_s = float(tt[0].item()), float(tt[1].item())
+        pipe_s, block_s = [float(x) for x in tt[:E2E_REPEATS]], [float(x) for x in tt[E2E_REPEATS:]]
+    e2e_s, e2e_block_s = float(np.median(pipe_s)), float(np.median(block_s))
     checksum = float(np.nansum(np.where(np.isfinite(h_out.numpy()), h_out.numpy(), 0.0)))
     same = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy(), equal_nan=True))
 
@@ -339,7 +365,8 @@ def run_ours(args, rank, world, local_rank):
     survey = None
     if not args.no_survey:
         from carma_pack_b200 import synth
-        ncv, nyc = args.survey_curves, 1000
+        # BASELINE config 5 is a FIXED survey (10^6 curves) spread over the GPUs: strong scaling
+        ncv, nyc = max(1, args.survey_curves // world), 1000
         sv_ms, sv_err, t_gen, sv_finite, ms_ = 0.0, None, 0.0, 0.0, None
         try:
             rng = np.random.default_rng(5000 + rank)
@@ -382,6 +409,7 @@ def run_ours(args, rank, world, local_rank):
         else:
             survey = {"metric": "multi light-curve LogDensity, CARMA(3,1), ny=1000, one theta per curve",
                       "value": world * ncv / (sv_ms * 1e-3), "unit": "curves/s", "curves_per_gpu": ncv, "ms": sv_ms,
+                      "curves_total": world * ncv, "scaling": "strong (the survey is split over the ranks, max-over-ranks time)",
                       "hbm_gbs_algorithmic": ncv * nyc * 24 / (sv_ms * 1e-3) / 1e9,
                       "tflops_algorithmic": ncv * f_eval(3, nyc) / (sv_ms * 1e-3) / 1e12,
                       "finite": sv_finite,
@@ -426,6 +454,33 @@ def run_ours(args, rank, world, local_rank):
             if sl is not None:
                 sl.close()
 
+    # ---- choose_order secondary (BASELINE config 4): pmax = 7 (28 models) x 100 random starts on an ny = 500 series;
+    # the (model, start) grid is sharded over the ranks by cost and only per-model summaries are all-gathered
+    order = None
+    if not args.no_order:
+        o_err, o_wall, o_sel, o_best = None, 0.0, None, None
+        try:
+            from carma_pack_b200 import synth
+            t5, y5, e5 = synth.readme_series(500, 500)
+            model = C.CarmaModel(t5, y5, e5, device=dev)
+            model.choose_order(2, ntrials=8, seed=1, verbose=False, dist=dist)   # warm-up: module load, series, streams
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            best, pq, aicc = model.choose_order(7, ntrials=args.order_trials, seed=500, verbose=False, dist=dist)
+            o_wall = time.perf_counter() - t0
+            o_sel, o_best = [int(model.p), int(model.q)], float(np.min(aicc))
+            aicc_table = [float(a) for a in aicc]
+        except Exception as ex:  # noqa: BLE001
+            o_err = "%s: %s" % (type(ex).__name__, ex)
+        o_wall, o_failed = _reduce_secondary(dist, torch, o_wall * 1e3, o_err)
+        if o_failed:
+            order = {"error": o_err or "failed on another rank"}
+        else:
+            order = {"metric": "choose_order(pmax=7) wall time, 28 (p,q) models x %d starts, ny=500" % args.order_trials,
+                     "wall_s": o_wall * 1e-3, "selected_pq": o_sel, "best_aicc": o_best, "aicc": aicc_table,
+                     "scaling": "strong (one grid, sharded over %d rank(s) by cost)" % world}
+
     clocks = sampler.stop() if sampler else None
 
     # ---- NCCL: gather per-rank summaries only (no data-path collective)
@@ -451,46 +506,84 @@ def run_ours(args, rank, world, local_rank):
         # CPU baseline beside it: oracle port, one core, the same 65,536-row batch (about 5-8 s)
         cpu = None
         if not args.no_cpu:
-            rate1 = float(np.mean([cpu_oracle_rate(t, y, e, th, 1) for _ in range(3)]))
+            rate1 = float(np.mean([cpu_oracle_rate(t, y, e, th, 1) for _ in range(2)]))
+            lean1 = float(cpu_oracle_rate(t, y, e, th, 1, lean=True))
             cpu = {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "the full 65,536-row theta batch of one step, three passes (about 10 s), one core, "
-                             "oracle/carma_oracle.cpp built -O3 -march=x86-64-v3"}
+                   "variant": "dense as-written (per-call vector copies, full p x p complex products): the reference's cost profile",
+                   "lean_variant_value": lean1,
+                   "lean_variant": "same arithmetic in the same order (bitwise equal results), fixed-size arrays, no heap in the time loop",
+                   "sample": "the full 65,536-row theta batch of one step: two passes dense + one pass lean (about 10 s), one "
+                             "core, oracle/carma_oracle.cpp built -O3 -march=x86-64-v3"}
+        # ---- roofline of the dominant (only) kernel of the step.  Three readings, all against the FP64 FMA peak
+        # measured on this GPU in this process:
+        #   frac            ALGORITHMIC flops (Hermitian complex P, 20p^2+36p+7 per step) on the IN-PRIOR rows
+        #                   only (rows outside the prior leave after the prologue and are not credited);
+        #   frac_executed   FP64 flops the kernel actually executes (per-step DFMA/DMUL/DADD counts read from the SASS of
+        #                   this build, profiles/r02_sass_loop_counts.json): the real-half state needs ~0.41x the
+        #                   algorithmic count, so `frac` overstates how busy the pipe is;
+        #   pipe_fp64_pct   sm__inst_executed_pipe_fp64 of the ncu capture of the same build (profiles/).
+        counts = {}
+        try:
+            counts = json.load(open(os.path.join(ROOT, "profiles", "r02_sass_loop_counts.json")))["k1"][str(P)]["all_conjugate_loop"]
+        except Exception:
+            pass
+        fin_kern_ms = in_prior["ms_per_step_rank0"]
+        achieved_fin_tf = in_prior["rows_rank0"] * fe / (fin_kern_ms * 1e-3) / 1e12
+        exec_flops_step = counts.get("fp64_flops")
+        PROLOGUE_FP64_FLOPS = 4300.0   # ~2,500 FP64 instructions of transform_theta<5> (SASS count, FMA = 2)
+        executed_tf = (in_prior["rows_rank0"] * ((NY - 1) * exec_flops_step + PROLOGUE_FP64_FLOPS) / (fin_kern_ms * 1e-3) / 1e12
+                       if exec_flops_step else None)
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_k1_ncu_summary.json")))
+        except Exception:
+            pass
+        roofline = {
+            "bound": "fp64", "achieved": achieved_fin_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_fin_tf / fp64_peak if fp64_peak else None,
+            "frac_definition": "algorithmic flops (SURVEY 8d) of the in-prior rows / measured FP64 FMA peak; the algorithmic "
+                               "count assumes a Hermitian complex P and overstates the executed work ~2.4x",
+            "achieved_all_rows": achieved_tf, "frac_all_rows": achieved_tf / fp64_peak if fp64_peak else None,
+            "executed_tflops": executed_tf, "frac_executed": executed_tf / fp64_peak if (executed_tf and fp64_peak) else None,
+            "executed_flops_per_step": exec_flops_step, "executed_fp64_instructions_per_step": counts.get("fp64_instructions"),
+            "instructions_per_step": counts.get("instructions"),
+            "dispatch_cycle_model_per_step": counts.get("dispatch_cycle_model"),
+            "executed_source": "profiles/r02_sass_loop_counts.json (scripts/sass_loopstat.py on this build), all-conjugate loop, P=5",
+            "pipe_fp64_pct": ncu.get("sm__inst_executed_pipe_fp64_pct"), "issue_active_pct": ncu.get("issue_active_pct"),
+            "pipe_source": ncu.get("source"),
+            "frac_of_datasheet": achieved_fin_tf / 40.0, "datasheet_peak": 40.0,
+            "datasheet_note": "B200 vector FP64 as published (40 TFLOP/s; SURVEY 8d asks for both)",
+            "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("traffic_source"),
+            "kernel": "loglik_batch_kernel<5>", "kernel_ms": kern_ms, "kernel_ms_in_prior_rows": fin_kern_ms,
+            "flops_per_eval": fe, "flops_per_step_formula": "20p^2+36p+7 (SURVEY 8d), transcendentals excluded",
+            "peak_source": "DFMA saturation micro-benchmark run on this GPU in this process (carma_fp64_peak_tflops); "
+                           "MEASURED_PEAKS.json has no FP64 entry; a recorded copy with clocks is profiles/FP64_PEAK.json",
+            "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched log-likelihood: 65,536 CARMA(5,3) parameter vectors on one ny=270 "
-                                   "series per GPU (BASELINE config 2)", "p": P, "q": Q, "ny": NY,
-                       "thetas_per_gpu": NTHETA, "l2": "256 MB buffer written between timed steps (outside the event pairs)",
-                       "timing": "CUDA events on the launching stream, per step; sum over K steps; max over ranks"},
+            "config": workload_config(),
+            "timing": {"l2": "256 MB buffer written between timed steps (outside the event pairs)",
+                       "how": "CUDA events on the launching stream, per step; sum over K steps; max over ranks"},
             "clocks": clocks,
             "e2e": {"value": world * NTHETA * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": NTHETA * d * 8,
                     "d2h_bytes_per_step": NTHETA * 8,
                     "api": "carma_loglik_batch_async/_wait: two-slot pipeline over pinned host buffers, K steps",
+                    "repeats": E2E_REPEATS, "statistic": "median over repeats of the K-step region (max over ranks per repeat)",
+                    "repeat_values": [world * NTHETA * K / x for x in pipe_s],
                     "blocking_call_value": world * NTHETA * K / e2e_block_s,
                     "blocking_api": "carma_loglik_batch (one synchronous call per step)",
                     "matches_device_path": same},
             "gpu_launches": K,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                         "frac_of_datasheet": achieved_tf / 40.0, "datasheet_peak": 40.0,
-                         "datasheet_note": "B200 vector FP64 as published (40 TFLOP/s; SURVEY 8d asks for both)",
-                         "traffic": 18.85e6, "traffic_source": "bytes per launch, dram__bytes_read.sum (15.94e6) + "
-                         "dram__bytes_write.sum (2.92e6) of one ncu --set full capture of this command "
-                         "(profiles/r01j_k1_ncu_key_metrics.csv); back-to-back launches without the L2 flush move "
-                         "6-10e6 (profiles/r01j_k1_traffic_launches.csv); algorithmic bytes are 6.3e6, the rest is the "
-                         "prologue's per-thread local-memory frame (0.6 kB x 65,536 threads)",
-                         "kernel": "loglik_batch_kernel<5>", "kernel_ms": kern_ms,
-                         "flops_per_eval": fe, "flops_per_step_formula": "20p^2+36p+7 (SURVEY 8d), transcendentals excluded",
-                         "peak_source": "DFMA saturation micro-benchmark run on this GPU in this process "
-                                        "(carma_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
-                         "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
-                                 "algorithmic_bytes_per_launch": alg_bytes,
-                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "in_prior_subset": in_prior,
             "pt_mcmc": pt,
+            "choose_order": order,
             "survey": survey,
             "scan": scan,
             "summary": {"max_logpost": summary[0], "finite_rows": summary[1], "checksum_rank0": checksum},
@@ -511,7 +604,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU baseline")
     ap.add_argument("--no-survey", action="store_true", help="skip the multi light-curve secondary measurement")
     ap.add_argument("--no-scan", action="store_true", help="skip the ny=1e6 associative-scan measurement")
-    ap.add_argument("--survey-curves", type=int, default=1000000)
+    ap.add_argument("--no-order", action="store_true", help="skip the choose_order (config 4) secondary measurement")
+    ap.add_argument("--order-trials", type=int, default=100)
+    ap.add_argument("--survey-curves", type=int, default=1000000, help="curves of the WHOLE survey (split over the ranks)")
     ap.add_argument("--scan-ny", type=int, default=1000000)
     ap.add_argument("--pt-ensembles", type=int, default=4096)
     ap.add_argument("--pt-iters", type=int, default=400)

@@ -475,7 +475,7 @@ def tdist_dev(seed, chain, it, j, dof=8):
 
 def fastmath_dev(rate, dt):
     """The time loop's transcendentals (csrc/fast_math.cuh) on arrays: rate in table steps per unit time.
-    Returns exp(rate dt ln2/32), sin and cos(rate dt pi/64), (1-rho)/2 and (1+rho)/2 with rho = the exponential, 1/rate."""
+    Returns exp(rate dt ln2/64), sin and cos(rate dt pi/64), (1-rho)/2 and (1+rho)/2 with rho = the exponential, 1/rate."""
     rate, dt = _c(rate), _c(dt)
     outs = [np.empty(rate.size) for _ in range(6)]
     check(lib.carma_fastmath_dev(_ptr(rate), _ptr(dt), rate.size, *[_ptr(o) for o in outs]), "carma_fastmath_dev")

@@ -143,8 +143,7 @@ struct KalmanReal {
         if (ODD) D[idx(P - 1, P - 1)] *= fo * fo;
 
         // ---- predicted observation: g = D c + h, var = c.g + e2, mean = c.z with c = (1,0,1,0,...[,1])
-        // mul_rn: never contracted into the following add, so both loop variants round identically
-        double m = z[0], vv = mul_rn(prm.scale, e2n);
+        double m = z[0];
 #pragma unroll
         for (int i = 0; i < P; i++) {
             double acc = prm.h[i];
@@ -153,9 +152,13 @@ struct KalmanReal {
                 if ((j & 1) == 0) acc += D[(i <= j) ? idx(i, j) : idx(j, i)];
             g[i] = acc;
         }
+        double vv = fma(prm.scale, e2n, g[0]);  // var = scale e2 + g_0 + g_2 + ...
 #pragma unroll
-        for (int i = 0; i < P; i++)
-            if ((i & 1) == 0) { vv += g[i]; if (i > 0) m += z[i]; }
+        for (int i = 2; i < P; i++)
+            if ((i & 1) == 0) vv += g[i];
+#pragma unroll
+        for (int i = 2; i < P; i++)
+            if ((i & 1) == 0) m += z[i];
         var = vv;
         mean = m;
     }
@@ -175,7 +178,7 @@ struct LogLikAcc {
     // some var was zero, negative, subnormal, infinite or NaN: exponent field 0 or 2047, or sign set
     CARMA_HD bool bad() const { return hmin < 0x00100000u || hmax >= 0x7ff00000u; }
     CARMA_HD void add(double var, double innov, double inv_var) {
-        quad = fma(innov * innov, inv_var, quad);
+        quad = fma(innov, innov * inv_var, quad);  // innov * inv_var is also the gain factor of the measurement update
         const int hi = hi32(var);
         prod *= mk64((hi & 0x000fffff) | 0x3ff00000, lo32(var));
         esum += (int)((unsigned)hi >> 20);

@@ -42,10 +42,10 @@ __host__ __device__ inline int model_dim(int kind, int p, int q) {
 
 template <int P>
 struct RealParams {
-    // Rates pre-multiplied by the table step of fast_math.cuh (32/ln2 for decays, 64/pi for phases):
-    //   slot s < P/2, conjugate pair w, conj(w): le[s] = Re w * 32/ln2,      ls[s] = Im w * 64/pi  (first root: Im <= 0)
-    //                 real pair w_b < w_a < 0  : le[s] = w_a * 32/ln2,       ls[s] = (w_b - w_a) * 32/ln2  (<= 0)
-    //   odd P: le[P/2] = w_{P-1} * 32/ln2
+    // Rates pre-multiplied by the table step of fast_math.cuh (64/ln2 for decays, 64/pi for phases):
+    //   slot s < P/2, conjugate pair w, conj(w): le[s] = Re w * 64/ln2,      ls[s] = Im w * 64/pi  (first root: Im <= 0)
+    //                 real pair w_b < w_a < 0  : le[s] = w_a * 64/ln2,       ls[s] = (w_b - w_a) * 64/ln2  (<= 0)
+    //   odd P: le[P/2] = w_{P-1} * 64/ln2
     // Components: conjugate pair -> (Re, Im) of the MA-normalised rotated state; real pair -> (x_a + x_b, x_a - x_b);
     // the observation is the sum of the FIRST component of every slot (+ the odd root's), for every kind of slot.
     double le[(P + 1) / 2];
@@ -62,7 +62,7 @@ __host__ __device__ constexpr double obs_c(int k) { return ((k & 1) == 0) ? 1.0 
 
 // Largest |rate * dt| in table steps the range reductions accept: rates are clamped to it in transform_theta
 // (dt_max = the longest gap of the series).  Unreachable inside the prior (|w| <= 2 pi / dt_min) unless
-// dt_max / dt_min > 2e6; beyond it e^{w dt} differs from 0 by less than e^{-2^30 ln2/32 dt_min/dt_max}.
+// dt_max / dt_min > 2e6; beyond it e^{w dt} differs from 0 by less than e^{-2^30 ln2/64 dt_min/dt_max}.
 constexpr double RATE_CAP_STEPS = 1073741824.0;         // 2^30: exp, k fits an int
 constexpr double PHASE_CAP_STEPS = 1125899906842624.0;  // 2^50: sin/cos, t = x + MAGIC exact
 

@@ -265,8 +265,8 @@ int carma_tdist_dev(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t j, in
 
 /* The branch-free transcendentals of the Kalman time loop (csrc/fast_math.cuh), evaluated element-wise on host
  * arrays so tests can bound their error against libm.  rate is in TABLE STEPS per unit time, as the loop holds it
- * (lambda * 32/ln2 for a decay, Im(omega) * 64/pi for a phase):
- *   out_exp      = exp(rate dt ln2/32)                        (rate <= 0)
+ * (lambda * 64/ln2 for a decay, Im(omega) * 64/pi for a phase):
+ *   out_exp      = exp(rate dt ln2/64)                        (rate <= 0)
  *   out_sin/cos  = sin, cos(rate dt pi/64)                    (NaN if the all-conjugate and generic variants differ)
  *   out_sh/ch    = (1 - rho)/2, (1 + rho)/2, rho = out_exp    (transition of a real root pair)
  *   out_rcp      = 1 / rate */

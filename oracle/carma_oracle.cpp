@@ -768,6 +768,75 @@ inline void chol_update_r1(double* L, double* v, int d, bool downdate) {
 // ===================================================================================
 // C entry points (ctypes)
 // ===================================================================================
+// "Lean" CPU variant of the same LogDensity: identical arithmetic in the identical order,
+// but the filter state lives in fixed-size arrays (no heap traffic, no per-call vector copies, loops with
+// compile-time bounds), mean/var are consumed on the fly instead of stored.  It bounds from above what the
+// reference's algorithm can do on one core; the dense variant above is the one that mirrors its cost profile.
+template <int P>
+static double lean_filter_loglik(const double* dt, const double* y, const double* yerr, size_t ny, double sigsqr,
+                                 const std::vector<cx<double>>& omega_v, const std::vector<double>& ma_v, double scale, double mu) {
+    using C = cx<double>;
+    C omega[P], b[P], x[P], K[P], rho[P], V[P][P], Pm[P][P];
+    double ma[P];
+    for (int i = 0; i < P; i++) { omega[i] = omega_v[i]; ma[i] = i < (int)ma_v.size() ? ma_v[i] : 0.0; x[i] = C(0, 0); }
+    std::vector<C> E((size_t)P * P), J(P, C(0, 0));
+    for (int k = 0; k < P; k++) E[k] = C(1, 0);
+    if (P > 1) for (int k = 0; k < P; k++) E[(size_t)P + k] = omega[k];
+    for (int i = 2; i < P; i++)
+        for (int k = 0; k < P; k++) E[(size_t)i * P + k] = std::pow(omega[k], double(i));
+    J[P - 1] = C(1, 0);
+    if (!lu_solve<double>(E, P, J)) return -std::numeric_limits<double>::infinity();
+    for (int k = 0; k < P; k++) {
+        C s(0, 0);
+        for (int i = 0; i < P; i++) s += ma[i] * E[(size_t)i * P + k];
+        b[k] = s;
+    }
+    for (int i = 0; i < P; i++)
+        for (int j = i; j < P; j++) V[i][j] = -sigsqr * J[i] * std::conj(J[j]) / (omega[i] + std::conj(omega[j]));
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < i; j++) V[i][j] = std::conj(V[j][i]);
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < P; j++) Pm[i][j] = V[i][j];
+    auto quad = [&](C (*M)[P]) {
+        C tot(0, 0);
+        for (int j = 0; j < P; j++) {
+            C bM(0, 0);
+            for (int i = 0; i < P; i++) bM += b[i] * M[i][j];
+            tot += bM * std::conj(b[j]);
+        }
+        return tot.real();
+    };
+    const double ssc = std::sqrt(scale);
+    double mean = 0.0, e0 = ssc * yerr[0];
+    double var = quad(V) + e0 * e0;
+    double innovation = y[0] - mu;
+    double ll = 0.0;
+    for (size_t cur = 1;; cur++) {
+        const double yc = y[cur - 1] - mean - mu;
+        ll += -0.5 * std::log(var) - 0.5 * yc * yc / var;
+        if (cur == ny) break;
+        for (int i = 0; i < P; i++) {
+            C s(0, 0);
+            for (int j = 0; j < P; j++) s += Pm[i][j] * std::conj(b[j]);
+            K[i] = s / var;
+        }
+        for (int i = 0; i < P; i++) x[i] += K[i] * innovation;
+        for (int i = 0; i < P; i++)
+            for (int j = 0; j < P; j++) Pm[i][j] -= var * (K[i] * std::conj(K[j]));
+        for (int i = 0; i < P; i++) rho[i] = std::exp(omega[i] * dt[cur - 1]);
+        for (int i = 0; i < P; i++) x[i] = rho[i] * x[i];
+        for (int i = 0; i < P; i++)
+            for (int j = 0; j < P; j++) Pm[i][j] = (rho[i] * std::conj(rho[j])) * (Pm[i][j] - V[i][j]) + V[i][j];
+        C m(0, 0);
+        for (int i = 0; i < P; i++) m += b[i] * x[i];
+        mean = m.real();
+        const double ec = ssc * yerr[cur];
+        var = quad(Pm) + ec * ec;
+        innovation = (y[cur] - mu) - mean;
+    }
+    return ll;
+}
+
 extern "C" {
 
 struct oracle_prior { double max_stdev, max_freq, min_freq, kappa_low, kappa_high, measerr_dof; };
@@ -883,6 +952,36 @@ void oracle_logdensity_batch_ld(int kind, int p, int q, const double* t, const d
     for (size_t i = 0; i < n; i++) {
         for (int j = 0; j < d; j++) th[j] = (long double)theta[i * (size_t)d + j];
         out[i] = (double)m.log_density(th.data());
+    }
+}
+
+// CARMA kinds with p >= 2 only (the benchmark shape); same bounds / theta transform / prior code as the dense variant.
+void oracle_logdensity_batch_lean(int kind, int p, int q, const double* t, const double* y, const double* yerr, size_t ny,
+                                  const oracle_prior* pr_, int ignore_prior, const double* theta, size_t n, double* out) {
+    const Prior pr = to_prior(pr_);
+    std::vector<double> dt(ny > 1 ? ny - 1 : 0);
+    for (size_t i = 0; i + 1 < ny; i++) dt[i] = t[i + 1] - t[i];
+    const int d = (kind == KIND_CARMA) ? 3 + p + q : (kind == KIND_ZCARMA ? 4 + p : 3 + p);
+    std::vector<cx<double>> omega;
+    for (size_t r = 0; r < n; r++) {
+        const double* th = theta + r * (size_t)d;
+        if (p < 2 || p > 7 || !check_prior_bounds<double>(kind, th, p, pr, ignore_prior != 0)) {
+            out[r] = -std::numeric_limits<double>::infinity();
+            continue;
+        }
+        quad_roots<double>(th + 3, p, omega);
+        std::vector<double> ma = extract_ma<double>(kind, th, p, q, pr);
+        const double sigsqr = th[0] * th[0] / carma_variance<double>(omega, ma, 1.0, 0.0);
+        double ll;
+        switch (p) {
+            case 2: ll = lean_filter_loglik<2>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+            case 3: ll = lean_filter_loglik<3>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+            case 4: ll = lean_filter_loglik<4>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+            case 5: ll = lean_filter_loglik<5>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+            case 6: ll = lean_filter_loglik<6>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+            default: ll = lean_filter_loglik<7>(dt.data(), y, yerr, ny, sigsqr, omega, ma, th[1], th[2]); break;
+        }
+        out[r] = ll + log_prior<double>(kind, th, p, pr);
     }
 }
 

@@ -185,8 +185,8 @@ def predict1(t, y, yerr, sigsqr, omega, tq):
     return qm, qv
 
 
-def logdensity(kind, p, q, t, y, yerr, theta, prior=None, ignore_prior=False, long_double=False, fast=False):
-    """CARMA_Base::LogDensity for each row of theta (n x d)."""
+def logdensity(kind, p, q, t, y, yerr, theta, prior=None, ignore_prior=False, long_double=False, fast=False, lean=False):
+    """CARMA_Base::LogDensity for each row of theta (n x d).  lean: the fixed-size, heap-free variant (p >= 2)."""
     t_, tp = _d(t)
     y_, yp = _d(y)
     e_, ep = _d(yerr)
@@ -197,7 +197,7 @@ def logdensity(kind, p, q, t, y, yerr, theta, prior=None, ignore_prior=False, lo
         prior = default_prior(t_, y_)
     out = np.empty(th.shape[0])
     L = lib(fast)
-    fn = L.oracle_logdensity_batch_ld if long_double else L.oracle_logdensity_batch
+    fn = L.oracle_logdensity_batch_ld if long_double else (L.oracle_logdensity_batch_lean if lean else L.oracle_logdensity_batch)
     fn(kind, p, q, tp, yp, ep, ctypes.c_size_t(t_.size), ctypes.byref(prior), int(ignore_prior),
        th.ctypes.data_as(_dp), ctypes.c_size_t(th.shape[0]), out.ctypes.data_as(_dp))
     return out

@@ -1,7 +1,8 @@
 """K1 cost model probe: time loglik_batch_kernel<P> (65,536 theta, device-resident) on the README-style series
 truncated to several lengths; a linear fit  t(ny) = prologue + (ny - 1) * step  separates the theta-transform
 prologue (+ launch, tail) from the per-Kalman-step cost.  Also reports the all-conjugate batch against a batch in
-which half of the rows have one real root pair (generic loop).  One JSON line.
+which half of the rows have one real root pair (generic loop); both with CARMA_IGNORE_BOUNDS so that every row runs
+the whole recursion.  One JSON line.
 
     python scripts/k1_probe.py [p] [q]
 """
@@ -37,14 +38,14 @@ for name, batch in (("ms", th), ("ms_mixed", th_mixed)):
         s = C.Series(t[:ny], y[:ny], e[:ny])
         pr = C.Series(t[:270], y[:270], e[:270]).default_prior()   # same prior bounds at every length
         for _ in range(3):
-            s.loglik_dev(kind, p, q, d_theta.data_ptr(), d_out.data_ptr(), N, pr, 0, stream)
+            s.loglik_dev(kind, p, q, d_theta.data_ptr(), d_out.data_ptr(), N, pr, C.IGNORE_BOUNDS, stream)
         torch.cuda.synchronize()
         best = []
         for _ in range(7):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            s.loglik_dev(kind, p, q, d_theta.data_ptr(), d_out.data_ptr(), N, pr, 0, stream)
+            s.loglik_dev(kind, p, q, d_theta.data_ptr(), d_out.data_ptr(), N, pr, C.IGNORE_BOUNDS, stream)
             e1.record()
             torch.cuda.synchronize()
             best.append(e0.elapsed_time(e1))

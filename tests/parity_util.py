@@ -5,8 +5,8 @@ fall in the same class.  For parameter vectors where the REFERENCE algorithm its
 tolerance (near-degenerate AR roots: the oracle's own result moves by more than the tolerance when it is re-evaluated
 in long double, or with theta moved by one or two ulps) the comparison is made against that measured noise floor.
 Every use of that escape hatch is RECORDED: number of rows, worst err/noise ratio, per call site.  The records are
-printed in the pytest terminal summary (also under -q) and written to tests/_parity_report.json and, when the
-directory exists, gpurun_out/parity_report.json."""
+printed in the pytest terminal summary (also under -q) and written to tests/_parity_report_{gpu,cpu}.json and, when
+the directory exists, gpurun_out/parity_report_{gpu,cpu}.json."""
 import json
 import os
 
@@ -78,9 +78,11 @@ def write_report(root):
     out = {"rtol": RTOL, "criterion": "err <= rtol*max(|lp|,1), else err <= 50 x measured oracle noise floor", "calls": REPORT,
            "total_noise_floor_rows": int(sum(r["noise_floor_rows"] for r in REPORT)),
            "total_rows": int(sum(r["rows"] for r in REPORT))}
-    paths = [os.path.join(root, "tests", "_parity_report.json")]
+    # the GPU suite and the CPU (host-compiled kernels) suite keep separate files
+    tag = "gpu" if any(not r["what"].startswith("host:") for r in REPORT) else "cpu"
+    paths = [os.path.join(root, "tests", "_parity_report_%s.json" % tag)]
     if os.path.isdir(os.path.join(root, "gpurun_out")):
-        paths.append(os.path.join(root, "gpurun_out", "parity_report.json"))
+        paths.append(os.path.join(root, "gpurun_out", "parity_report_%s.json" % tag))
     for p in paths:
         try:
             with open(p, "w") as f:

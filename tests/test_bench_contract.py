@@ -9,8 +9,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    # run through runpy so that the loaded modules can be inspected afterwards: the reference arm must not import the
+    # product package (that would load libcarma_b200.so into the process the driver inspects)
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "bad = [m for m in sys.modules if m.split('.')[0] in ('carma_pack_b200', 'carmcmc', 'torch')]\n"
+            "loaded = open('/proc/self/maps').read()\n"
+            "assert not bad, bad\n"
+            "assert 'libcarma_b200' not in loaded and '_carmcmc' not in loaded\n") % os.path.join(ROOT, "bench.py")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -25,6 +33,11 @@ def test_reference_arm_prints_one_contract_line():
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the same config object as the GPU arm prints (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config()
+    assert cb["lean_variant_value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():

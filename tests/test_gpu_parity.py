@@ -171,8 +171,9 @@ def test_loglik_config2_65536_thetas(C, O):
     want = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr)
     assert 0.5 < np.isfinite(want).mean() < 1.0  # both the filter path and the -inf early-out are exercised
     want_ld = O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, th, prior=opr, long_double=True)
+    # audited ceiling: at most 40 of the 65,536 rows may need the noise-floor criterion (round 2 observed: ~20)
     n_ill = assert_logpost_parity(
-        got, want, want_ld, what="config2",
+        got, want, want_ld, what="config2", max_illcond_rows=40,
         ulp_eval=lambda rows, k: O.logdensity(O.KIND_CARMA, 5, 3, t, y, e, ulp_shift(th[rows], k), prior=opr))
     print("config2: %d of 65536 rows used the noise-floor criterion" % n_ill)
     # idempotence / determinism: same input, same bits
@@ -239,10 +240,11 @@ def test_loglik_stress_all_orders(C, O):
                 want = O.logdensity(okind, p, q, t, y, e, th, prior=opr, ignore_prior=ign)
                 want_ld = O.logdensity(okind, p, q, t, y, e, th, prior=opr, ignore_prior=ign, long_double=True)
                 total_ill += assert_logpost_parity(
-                    got, want, want_ld, max_illcond_frac=0.15, what="stress p=%d q=%d ign=%d" % (p, q, ign),
+                    got, want, want_ld, max_illcond_frac=0.08, what="stress p=%d q=%d ign=%d" % (p, q, ign),
                     ulp_eval=lambda rows, k: O.logdensity(okind, p, q, t, y, e, ulp_shift(th[rows], k), prior=opr,
                                                           ignore_prior=ign))
     print("stress: %d rows needed the noise-floor criterion" % total_ill)
+    assert total_ill <= 120, total_ill   # of 7,950 rows over all orders (observed in round 2: ~45; 4 % in the worst (p,q))
     s.close()
 
 
@@ -358,7 +360,7 @@ def test_scan_kalman_matches_sequential_and_oracle(C, O):
             assert np.all(got[~fin] == seq[~fin])
             np.testing.assert_allclose(got[fin], seq[fin], rtol=1e-9, err_msg="%s chunk=%d vs sequential" % (kind_name, chunk))
             assert_logpost_parity(got, want, O.logdensity(okind, p, q, t, y, e, th, prior=opr, long_double=True),
-                                  max_illcond_frac=0.5, what="scan %s chunk=%d" % (kind_name, chunk),
+                                  max_illcond_frac=0.34, what="scan %s chunk=%d" % (kind_name, chunk),
                                   ulp_eval=lambda rows, k: O.logdensity(okind, p, q, t, y, e, ulp_shift(th[rows], k), prior=opr))
     s.close()
     # a long series: 200,000 points, CARMA(3,1), against the CPU oracle
@@ -385,9 +387,9 @@ def test_fast_math_accuracy(C):
     n = 40000
     lnat = -np.exp(rng.uniform(np.log(1e-6), np.log(50.0), n))
     dt = np.exp(rng.uniform(np.log(1e-2), np.log(30.0), n))
-    l_exp = lnat * (32.0 / np.log(2.0))
+    l_exp = lnat * (64.0 / np.log(2.0))
     ex, _, _, s_r, c_r, _ = C._lib.fastmath_dev(l_exp, dt)
-    x = l_exp.astype(np.longdouble) * dt.astype(np.longdouble) * (np.log(np.longdouble(2)) / 32)
+    x = l_exp.astype(np.longdouble) * dt.astype(np.longdouble) * (np.log(np.longdouble(2)) / 64)
     want = np.exp(x)
     ok = x > -700
     rel = np.abs(ex[ok] - want[ok]) / want[ok]

@@ -151,11 +151,11 @@ def test_loop_transcendentals(H):
     n = 40000
     lnat = -np.exp(rng.uniform(np.log(1e-6), np.log(50.0), n))          # natural rates
     dt = np.exp(rng.uniform(np.log(1e-2), np.log(30.0), n))
-    l_exp = lnat * (32.0 / np.log(2.0))
+    l_exp = lnat * (64.0 / np.log(2.0))
     outs = [np.empty(n) for _ in range(6)]
     H.hostcheck_fastmath(l_exp.ctypes.data_as(_dp), dt.ctypes.data_as(_dp), ctypes.c_size_t(n), *[o.ctypes.data_as(_dp) for o in outs])
     ex, _, _, s_r, c_r, _ = outs
-    x = l_exp.astype(np.longdouble) * dt.astype(np.longdouble) * (np.log(np.longdouble(2)) / 32)
+    x = l_exp.astype(np.longdouble) * dt.astype(np.longdouble) * (np.log(np.longdouble(2)) / 64)
     want = np.exp(x)
     ok = x > -700
     rel = np.abs(ex[ok] - want[ok]) / want[ok]
