@@ -296,7 +296,7 @@ class Series:
             res.update(ram_trace=rt, exchange_trace=xt, proposals=prop)
         return res
 
-    def mle_batch(self, kind, p, q, x0, lower, upper, prior=None, flags=0, maxiter=200, history=8, gtol=1e-5,
+    def mle_batch(self, kind, p, q, x0, lower, upper, prior=None, flags=0, maxiter=1000, history=8, gtol=1e-5,
                   ftol=2.2e-9, fd_eps=1e-8, slot=0):
         """Projected L-BFGS from every row of x0 in lock-step (carma_mle_batch): minimises -LogDensity over the
         box [lower, upper].  Returns (x, f, nit, nfev).  Releases the GIL for the whole fit."""
@@ -422,7 +422,7 @@ class MultiSeries:
               "carma_multi_loglik_dev")
 
 
-def lbfgs_batch(fun_batch, x0, lower, upper, maxiter=200, history=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
+def lbfgs_batch(fun_batch, x0, lower, upper, maxiter=1000, history=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
     """The native optimiser core (carma_lbfgs_batch) on a Python objective: fun_batch maps an (n, d) array to n
     values.  Host code only; this is the loop Series.mle_batch runs with the GPU log-density as objective."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)

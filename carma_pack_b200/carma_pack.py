@@ -35,7 +35,7 @@ class OptimizeResult(dict):
     __setattr__ = dict.__setitem__
 
 
-def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
+def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=1000, m=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8):
     """Minimise fun over a box for every row of x0 simultaneously.
 
     fun_batch maps an (n, d) array to n function values (non-finite values are treated as +inf).
@@ -85,6 +85,7 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
     S = np.zeros((m, n, d))
     Y = np.zeros((m, n, d))
     nh = np.zeros(n, dtype=int)
+    restarts_left = np.full(n, 2)   # history resets granted before a row may stop on "small decrease" / failed search
     active = f < big
     nit = 0
     rows = np.arange(n)
@@ -152,8 +153,14 @@ def batched_lbfgs(fun_batch, x0, lower, upper, maxiter=200, m=8, gtol=1e-5, ftol
         Y[nh[ci], ci] = yv[ci]
         nh[ci] += 1
         x, f, g = xn, fn, gn
-        active &= ~todo   # line search failed: stop that row
-        active &= ~small
+        # line search failed or negligible decrease: drop the row's history and go on (twice at most), then stop it
+        stop = (todo & active) | small
+        again = stop & (nh > 0) & (restarts_left > 0)
+        nh[again] = 0
+        S[:, again] = 0.0
+        Y[:, again] = 0.0
+        restarts_left[again] -= 1
+        active &= ~(stop & ~again)
     return x, f, nit, nfev
 
 
@@ -229,23 +236,17 @@ class CarmaModel(object):
             hi += [np.inf] * q
         return np.array(lo), np.array(hi)
 
-    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, trial_offset=0, series=None,
-                optimizer="native"):
-        """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
-        in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
-        global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
-        rank runs it).  series: device series to use (choose_order gives each worker thread its own).
-        optimizer: "native" = carma_mle_batch (C++ host loop, no interpreter in the iteration);
-        "python" = the same algorithm in numpy (batched_lbfgs), kept as the cross-check."""
+    def mle_starts(self, p, q, ntrials, seed, trial_offset=0, series=None):
+        """The `ntrials` starting points of get_mle and everything that defines the fits: (kind, x0, lower, upper,
+        prior, flags).  Start j depends only on (seed, trial_offset + j): short on-device MCMC runs with nsamples=1,
+        nburnin=25, nwalkers=10 as in the reference (carma_pack.py:197-216), measerr_scale set to 1 (:216), components
+        outside the optimiser's box redrawn uniformly inside it (:244-248)."""
         series = self.series if series is None else series
         kind = _kind_for(p, q)
         d = model_dim(kind, p, q)
-        if seed is None:
-            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
         prior = series.default_prior(population_var=True)
-        # initial guesses: nsamples=1, nburnin=25, nwalkers=10 MCMC runs (carma_pack.py:197-216)
         res = series.pt_run(kind, p, q, 1, 25, ntemps=1 if p == 1 else 10, n_ensembles=ntrials, seed=seed,
-                                 ensemble_offset=trial_offset, prior=prior)
+                            ensemble_offset=trial_offset, prior=prior)
         x0 = res["samples"][:, 0, :].copy()
         x0[:, 1] = 1.0  # carma_pack.py:216
         lo, hi = self._mle_bounds(p, q)
@@ -255,6 +256,20 @@ class CarmaModel(object):
                 if np.isfinite(lo[j]) and ((x0[i, j] < lo[j]) or (x0[i, j] > hi[j])):
                     x0[i, j] = rng.uniform(lo[j], hi[j])
         flags = 0 if p == 1 else IGNORE_BOUNDS  # SetMLE(True) only for p > 1 (carma_pack.py:242)
+        return kind, x0, lo, hi, prior, flags
+
+    def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=1000, trial_offset=0, series=None,
+                optimizer="native"):
+        """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
+        in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
+        global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
+        rank runs it).  series: device series to use (choose_order gives each worker thread its own).
+        optimizer: "native" = carma_mle_batch (C++ host loop, no interpreter in the iteration);
+        "python" = the same algorithm in numpy (batched_lbfgs), kept as the cross-check."""
+        series = self.series if series is None else series
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+        kind, x0, lo, hi, prior, flags = self.mle_starts(p, q, ntrials, seed, trial_offset=trial_offset, series=series)
 
         def negloglik(th):  # _carma_loglik, carma_pack.py:255-260
             # through the slot API: its own stream, so concurrent fits of other models overlap on the GPU
@@ -335,17 +350,20 @@ class CarmaModel(object):
         if world > 1:
             from . import sharding
             dmax = max(3 + p + q for p, q in pqlist)
-            table = np.full((len(pqlist), 2 + dmax), np.nan)
+            # row = [-loglik (selection key), nit, nfev, theta-hat..., nan padding]
+            table = np.full((len(pqlist), 3 + dmax), np.nan)
             table[:, 0] = np.inf
             for k, mle in local.items():
-                table[k, 0], table[k, 1] = mle.fun, mle.fun
-                table[k, 2:2 + len(mle.x)] = mle.x
-            best = sharding.best_aicc(table, dist)
+                table[k, 0], table[k, 1], table[k, 2] = mle.fun, mle.nit, mle.nfev
+                table[k, 3:3 + len(mle.x)] = mle.x
+            best = sharding.best_per_model(table, dist)
             MLEs = []
             for k, (p, q) in enumerate(pqlist):
                 d = 4 if p == 1 else 3 + p + q
-                MLEs.append(OptimizeResult(x=best[k, 2:2 + d].copy(), fun=float(best[k, 1]),
-                                           success=bool(np.isfinite(best[k, 1])), message="gathered"))
+                MLEs.append(OptimizeResult(x=best[k, 3:3 + d].copy(), fun=float(best[k, 0]), nit=int(best[k, 1]),
+                                           nfev=int(best[k, 2]), success=bool(np.isfinite(best[k, 0])),
+                                           message="batched projected L-BFGS, best over all ranks' starts (all_x / all_fun "
+                                                   "stay on the rank that ran them)"))
         else:
             MLEs = [local[k] for k in range(len(pqlist))]
         best_AICc, AICc, best_MLE = 1e300, [], MLEs[0]

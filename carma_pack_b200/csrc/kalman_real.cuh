@@ -54,8 +54,8 @@ struct KalmanReal {
     // variance `var`, move forward by dt, and form mean/var for the next point (measurement variance e2n).
     // ALLC = true: every 2x2 slot is a conjugate pair (compile time; the per-lane selections vanish);
     // ALLC = false: conjugate and real pairs mixed per lane -- same instruction sequence, operands selected.
-    template <bool ALLC>
-    CARMA_HD void advance(const RealParams<P>& prm, const MathTab& tb, double innov, double inv_var, double dt, double e2n) {
+    template <bool ALLC, class Tab>
+    CARMA_HD void advance(const RealParams<P>& prm, const Tab& tb, double innov, double inv_var, double dt, double e2n) {
         measurement_update(innov, inv_var);
         predict_observe<ALLC>(prm, tb, dt, e2n);
     }
@@ -76,8 +76,8 @@ struct KalmanReal {
     }
 
     // the transition blocks [[A, sB],[B, A]] of all slots and the factor of the odd root
-    template <bool ALLC>
-    static CARMA_HD void transition(const RealParams<P>& prm, const MathTab& tb, double dt, double* fa, double* fb,
+    template <bool ALLC, class Tab>
+    static CARMA_HD void transition(const RealParams<P>& prm, const Tab& tb, double dt, double* fa, double* fb,
                                     double* fsb, double* fo) {
 #pragma unroll
         for (int s = 0; s < NS; s++) {
@@ -95,8 +95,8 @@ struct KalmanReal {
     }
 
     // transition by dt and predicted observation of the next point (kfilter.cpp:200-210)
-    template <bool ALLC>
-    CARMA_HD void predict_observe(const RealParams<P>& prm, const MathTab& tb, double dt, double e2n) {
+    template <bool ALLC, class Tab>
+    CARMA_HD void predict_observe(const RealParams<P>& prm, const Tab& tb, double dt, double e2n) {
         double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
         transition<ALLC>(prm, tb, dt, fa, fb, fsb, &fo);
 
@@ -234,8 +234,8 @@ constexpr int RENORM_EVERY = 512;
 // only scored, not advanced past (end of the light curve).
 // PF = true: the three operands of step i+1 are loaded while step i is computed (software prefetch);
 // used when the series is read straight from global memory (K4, K5), pointless for shared memory.
-template <int P, bool ALLC, bool PF, class Src>
-CARMA_HD void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const MathTab& tb,
+template <int P, bool ALLC, bool PF, class Src, class Tab>
+CARMA_HD void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
                                const Src& src, int len, int nadv) {
     double y_c = 0.0, dt_c = 0.0, e_c = 0.0;
     if (PF && nadv > 0) src.get(0, &dt_c, &y_c, &e_c);
@@ -268,8 +268,8 @@ CARMA_HD void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealPara
     }
 }
 
-template <int P, bool PF, class Src>
-CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const MathTab& tb,
+template <int P, bool PF, class Src, class Tab>
+CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
                               const Src& src, int len, int nadv) {
     constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
 #ifdef __CUDA_ARCH__
@@ -286,8 +286,8 @@ CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParam
 
 // Exact (slow) evaluation of the log-likelihood of one theta: the same recursion with one log() per point.
 // Only reached when LogLikAcc::bad was raised (var not a positive normal number somewhere).
-template <int P, class Src>
-__host__ __device__ __noinline__ double loglik_exact_slow(const RealParams<P>& prm, const MathTab& tb, const Src& src,
+template <int P, class Src, class Tab>
+__host__ __device__ __noinline__ double loglik_exact_slow(const RealParams<P>& prm, const Tab& tb, const Src& src,
                                                           int ny, double e2_0) {
     KalmanReal<P> kf;
     kf.reset(prm, e2_0);

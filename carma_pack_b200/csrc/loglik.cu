@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 #include <limits>
+#include <type_traits>
 
 #include "kalman_real.cuh"
 #include "series.h"
@@ -154,13 +156,14 @@ cudaError_t launch_loglik_batch(const SeriesView& sv, int kind, int p, int q, un
 // ---------------------------------------------------------------------------------------------
 constexpr int K4_BLOCK = 64;
 
-template <int P>
+// GTAB: math tables read from global memory (default, see MathTabGlobal) instead of static shared memory
+template <int P, bool GTAB>
 __global__ void __launch_bounds__(K4_BLOCK)
 multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y, const double* __restrict__ e2,
                     const long long* __restrict__ off, size_t ncurves, double dt_max, int kind, int q, int d, unsigned flags,
                     const carma_prior_t* __restrict__ priors, const double* __restrict__ theta,
                     double* __restrict__ out) {
-    MathTab tb;
+    typename std::conditional<GTAB, MathTabGlobal, MathTab>::type tb;
     tb.load();
     const size_t c = (size_t)blockIdx.x * K4_BLOCK + threadIdx.x;
     if (c >= ncurves) return;
@@ -191,9 +194,14 @@ cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, in
                                 cudaStream_t stream) {
     int d = model_dim(kind, p, q);
     unsigned grid = (unsigned)((m->ncurves + K4_BLOCK - 1) / K4_BLOCK);
-#define LAUNCH_K4(PP)                                                                                             \
-    multi_loglik_kernel<PP><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, m->dt_max, \
-                                                           kind, q, d, flags, d_priors, d_theta, d_out)
+    static const bool smem_tab = [] { const char* e = getenv("CARMA_K4_TABLES"); return e && !strcmp(e, "smem"); }();
+#define LAUNCH_K4(PP)                                                                                                 \
+    if (smem_tab)                                                                                                     \
+        multi_loglik_kernel<PP, false><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, \
+                                                                      m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out); \
+    else                                                                                                              \
+        multi_loglik_kernel<PP, true><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves,  \
+                                                                     m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out)
     switch (p) {
         case 1: LAUNCH_K4(1); break;
         case 2: LAUNCH_K4(2); break;

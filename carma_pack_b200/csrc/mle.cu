@@ -25,7 +25,7 @@ using namespace carma;
 
 extern "C" void carma_mle_default_opts(carma_mle_opts_t* o) {
     if (!o) return;
-    o->maxiter = 200;
+    o->maxiter = 1000;
     o->history = 8;
     o->max_backtrack = 25;
     o->reserved = 0;
@@ -173,6 +173,10 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
     // whose newest (s, y) fails the curvature test simply keeps its previous pairs, so the result of a start never
     // depends on which other starts share the batch (and hence not on how the starts are sharded over GPUs).
     std::vector<int> nh(n, 0), h0(n, 0);
+    // A row that stops on the small-decrease rule or on a failed line search first gets its history dropped and
+    // continues from a scaled steepest-descent step (twice at most): with a poor quasi-Newton model one short Armijo
+    // step can look like convergence far from a stationary point.
+    std::vector<int> restarts_left(n, 2);
 
     for (size_t i = 0; i < n; i++)
         for (size_t j = 0; j < d; j++) x[i * d + j] = std::min(std::max(x0[i * d + j], lower[j]), upper[j]);
@@ -389,8 +393,15 @@ int lbfgs_core(Objective& ev, size_t n, size_t d, const double* x0, const double
         }
         for (size_t i = 0; i < n; i++) {
             const bool small = moved[i] && ((f[i] - fn[i]) <= o.ftol * std::max(std::max(std::fabs(f[i]), std::fabs(fn[i])), 1.0));
-            if (todo[i]) active[i] = 0;  // line search failed: stop that row
-            if (small) active[i] = 0;
+            if (todo[i] || small) {  // line search failed / negligible decrease
+                if (nh[i] > 0 && restarts_left[i] > 0) {
+                    nh[i] = 0;
+                    h0[i] = 0;
+                    restarts_left[i]--;
+                } else {
+                    active[i] = 0;
+                }
+            }
         }
         x = xn;
         f = fn;

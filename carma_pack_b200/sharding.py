@@ -38,9 +38,12 @@ def gather_summaries(local, dist=None):
     return np.stack([o.cpu().numpy() for o in out])
 
 
-def best_aicc(local_table, dist=None):
-    """local_table: (n_models, 2 + dmax) rows [AICc, -loglik, theta_hat..., nan padding], +inf AICc for
-    models this rank did not fit (or fitted worse).  Returns the element-wise best over ranks."""
+def best_per_model(local_table, dist=None):
+    """local_table: (n_models, 1 + k) rows [key, payload...] with key = -loglik of the best fit this rank found for
+    the model (+inf for models it did not fit); the payload travels with it (theta-hat, nit, nfev, nan padding).
+    Returns, per model, the row of the rank with the smallest key.  For a fixed model AICc is an increasing function
+    of -loglik, so this is also the rank with the best AICc; the AICc itself is computed by the caller afterwards."""
     allt = gather_summaries(local_table, dist)
     pick = np.argmin(allt[:, :, 0], axis=0)
     return allt[pick, np.arange(allt.shape[1])]
+

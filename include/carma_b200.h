@@ -127,7 +127,7 @@ int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* p
  * value was ever found); nit_out / nfev_out may be NULL.  slot: the stream slot of the series to use (0/1), so
  * fits driven from different host threads on different series handles overlap on the GPU. */
 typedef struct carma_mle_opts {
-    int maxiter;        /* 200 */
+    int maxiter;        /* 1000: L-BFGS-B stops on maxfun = 15000 evaluations, i.e. ~1000 finite-difference gradients at d = 14 */
     int history;        /* L-BFGS pairs kept, 8 */
     int max_backtrack;  /* Armijo halvings per iteration, 25 */
     int reserved;

@@ -270,6 +270,20 @@ def make_loglik_fixture():
     np.savez(os.path.join(HERE, "loglik_cases.npz"), **flat)
 
 
+def make_mcmc_fixtures():
+    """The reference's own 1000-point test series for the long statistical tests (posterior recovery within 3 sigma,
+    residual whiteness): cpp_tests/data/{car5,zcar5,carma}_test.dat with the true parameters of
+    cpp_tests/carma_unit_tests.cpp:1378-1656 / generate_test_data.py:47-58.  Data only (time, y, yerr)."""
+    out = {}
+    for name in ("car5", "zcar5", "carma"):
+        data = np.loadtxt(os.path.join(REF, "cpp_tests/data/%s_test.dat" % name))
+        out[name + "_t"], out[name + "_y"], out[name + "_yerr"] = data[:, 0], data[:, 1], data[:, 2]
+    out["qpo_width"] = np.array([0.01, 0.01, 0.002])
+    out["qpo_cent"] = np.array([0.2, 0.02])
+    out["sigmay"], out["kappa"] = np.array(2.3), np.array(0.5)
+    np.savez_compressed(os.path.join(HERE, "mcmc_fixtures.npz"), **out)
+
+
 def make_car1_fixture():
     """CAR(1): the reference has no numpy CAR(1) filter (KalmanFilter1 is C++-only and
     KalmanFilterDeprecated indexes row 1 of a 1x1 matrix), so CAR(1) is pinned the way the
@@ -310,3 +324,4 @@ if __name__ == "__main__":
     make_kelly_fixture()
     make_loglik_fixture()
     make_car1_fixture()
+    make_mcmc_fixtures()

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     m = C._lib.MLEOpts()
     C._lib.lib.carma_mle_default_opts(ctypes.byref(m))
     # scipy L-BFGS-B defaults used by the reference's fits (minimize(..., method="L-BFGS-B") at carma_pack.py:250): pgtol 1e-5, factr*eps 2.2e-9, eps 1e-8
-    assert (m.maxiter, m.history, m.max_backtrack) == (200, 8, 25)
+    assert (m.maxiter, m.history, m.max_backtrack) == (1000, 8, 25)
     assert (m.gtol, m.ftol, m.fd_eps) == (1e-5, 2.2e-9, 1e-8)
 
 

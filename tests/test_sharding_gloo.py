@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
                 table[mdl, 0] = aicc
                 table[mdl, 1] = aicc / 2
                 table[mdl, 2:] = u
-        best = sharding.best_aicc(table, dist)
+        best = sharding.best_per_model(table, dist)
         g = sharding.gather_summaries(np.array([float(rank), float(stop - start)]), dist)
         q.put((rank, best, g))
     finally:
@@ -102,7 +102,7 @@ def _fake_get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=200, tria
     d = 4 if p == 1 else 3 + p + q
     vals = [200.0 + 3.0 * abs(p - 3) + 1.5 * q + ((7 * (trial_offset + j) + 3 * p + q) % 11) * 0.1 for j in range(ntrials)]
     j = int(np.argmin(vals))
-    return OptimizeResult(x=np.full(d, float(trial_offset + j)), fun=float(vals[j]), success=True)
+    return OptimizeResult(x=np.full(d, float(trial_offset + j)), fun=float(vals[j]), success=True, nit=7, nfev=99)
 
 
 def _choose_order_worker(rank, world, port, q):
