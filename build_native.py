@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, "csrc")
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CXX = os.environ.get("CXX_HOST") or shutil.which("g++") or "g++"
 
-CUDA_SOURCES = ["loglik.cu", "mcmc.cu", "scan.cu", "sim.cu", "mle.cu"]
+CUDA_SOURCES = ["loglik.cu", "mcmc.cu", "scan.cu", "sim.cu", "mle.cu", "comm.cu"]
 CUDA_HEADERS = ["device_math.cuh", "fast_math.cuh", "theta_transform.cuh", "kalman_real.cuh", "kalman_cplx.cuh", "series.h",
                 os.path.join(ROOT, "include", "carma_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -68,7 +68,7 @@ def build_cuda(force=False, verbose=False):
     if verbose:
         for _, out in results:
             print(out)
-    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static"])
+    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-cudart", "static", "-ldl"])
     return LIB
 
 

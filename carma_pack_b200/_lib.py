@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = [
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
     "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
+    "carma_starting_value", "carma_comm_unique_id", "carma_comm_init_rank", "carma_comm_destroy",
+    "carma_gather_summaries", "carma_gather_summaries_dev",
 ]
 
 
@@ -125,6 +127,13 @@ def _load():
     L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
     L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
     L.carma_fastmath_dev.argtypes = [_dp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.carma_starting_value.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Prior), ctypes.c_uint64,
+                                       ctypes.c_uint32, ctypes.c_int, _dp, _dp]
+    L.carma_comm_unique_id.argtypes = [ctypes.c_char_p]
+    L.carma_comm_init_rank.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.carma_comm_destroy.argtypes = [_vp]
+    L.carma_gather_summaries.argtypes = [_vp, _dp, _sz, _dp, _vp]
+    L.carma_gather_summaries_dev.argtypes = [_vp, _vp, _sz, _vp, _vp]
     L.carma_tdist_dev.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _dp]
     return L
 

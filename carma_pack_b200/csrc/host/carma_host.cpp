@@ -7,6 +7,7 @@
 #include <iostream>
 #include <numeric>
 #include <random>
+#include <sstream>
 
 namespace carma_host {
 
@@ -146,9 +147,10 @@ void KalmanFilterp::params(double& sigsqr, vecC& omega, vecD& ma) const {
 // ---- CARMA_Base ------------------------------------------------------------------------------
 CARMA_Base::CARMA_Base(bool track, std::string name, const vecD& time, const vecD& y, const vecD& yerr, int kind, int p,
                        int q, double temperature)
-    : track_(track), name_(name), temperature_(temperature), kind_(kind), p_(p), q_(q),
+    : Parameter<vecD>(track, name, temperature), kind_(kind), p_(p), q_(q),
       series_(std::make_shared<DeviceSeries>(time, y, yerr)) {
     if (p < 1 || p > CARMA_MAX_P) throw std::invalid_argument("order p must be in 1..7");
+    value_.assign((size_t)Dimension(), 0.0);  // carpack.hpp:72: value_.set_size(p + 3)
     // carpack.hpp:71: SetPrior(10 sqrt(arma::var(y))) with the N-1 variance
     check(carma_series_default_prior(series_->handle(), 0, &prior_), "carma_series_default_prior");
 }
@@ -167,12 +169,53 @@ double CARMA_Base::LogPrior(const vecD& theta) const {
     return out;
 }
 
-double CARMA_Base::LogDensity(const vecD& theta) const {
+double CARMA_Base::LogDensity(vecD theta) {
     if ((int)theta.size() != Dimension()) throw std::invalid_argument("theta has the wrong length");
     double out = 0.0;
     check(carma_loglik_batch(series_->handle(), kind_, p_, q_, &prior_, 1, theta.data(), &out,
                              ignore_prior_ ? CARMA_IGNORE_BOUNDS : 0u), "carma_loglik_batch");
+    last_theta_ = theta;
+    last_logpost_ = out;
     return out;
+}
+
+void CARMA_Base::Save(vecD new_value) {
+    // carpack.hpp:90-108 sums the log-posterior over the mean / var the filter holds from the preceding
+    // LogDensity(new_value); a different value here means no such call was made, so evaluate it
+    const bool cached = new_value == last_theta_;
+    const double lp = cached ? last_logpost_ : LogDensity(new_value);
+    value_ = new_value;
+    log_posterior_ = lp;
+}
+
+vecD CARMA_Base::StartingValue() {
+    vecD theta((size_t)Dimension());
+    double lp = 0.0;
+    // a fresh Philox key per call (seeded by set_seed / the clock), the chain index separates the chains of an ensemble
+    check(carma_starting_value(series_->handle(), kind_, p_, q_, &prior_, next_run_seed() + start_draws_++, chain_, 1000,
+                               theta.data(), &lp), "carma_starting_value");
+    last_theta_ = theta;
+    last_logpost_ = lp;
+    return theta;
+}
+
+vecD CARMA_Base::SetStartingValue(vecD init) {
+    if ((int)init.size() != Dimension()) {
+        std::cout << "WARNING: initial guess wrong length, initializing with prior" << std::endl;
+        return StartingValue();
+    }
+    const double logpost = LogDensity(init);
+    if (!std::isfinite(logpost)) {
+        std::cout << "WARNING: initial guess yields non-finite likelihood, initializing with prior" << std::endl;
+        return StartingValue();
+    }
+    return init;
+}
+
+std::string CARMA_Base::StringValue() {
+    std::ostringstream ss;
+    for (size_t i = 0; i < value_.size(); i++) ss << (i ? " " : "") << value_[i];
+    return ss.str();
 }
 
 vecD CARMA_Base::LogDensityBatch(const vecvecD& theta) const {
@@ -188,7 +231,7 @@ vecD CARMA_Base::LogDensityBatch(const vecvecD& theta) const {
     return out;
 }
 
-bool CARMA_Base::CheckPriorBounds(const vecD& theta) const {
+bool CARMA_Base::CheckPriorBounds(const vecD& theta) {
     if (ignore_prior_ && kind_ != CARMA_KIND_CAR1) return true;
     double lp = LogDensity(theta);
     return !(std::isinf(lp) && lp < 0);
@@ -228,6 +271,53 @@ double CARp::Variance(const vecC& r, const vecD& ma, double sigma, double dt) co
         total += s1 * s2 * std::exp(r[k] * dt) / (-2.0 * r[k].real() * dp);
     }
     return sigma * sigma * total.real();
+}
+
+vecD CARp::ExtractMA(const vecD& theta) const {  // carpack.hpp:314, 335: [1, 0, ..., 0] (also what ZCAR evaluates)
+    (void)theta;
+    vecD ma((size_t)p_, 0.0);
+    ma[0] = 1.0;
+    return ma;
+}
+
+vecD CARMA::ExtractMA(const vecD& theta) const {  // carpack.cpp:522-580 with polycoefs (742-756)
+    vecD ma((size_t)p_, 0.0);
+    ma[0] = 1.0;
+    if (q_ == 0) return ma;
+    vecC roots((size_t)q_);
+    for (int i = 0; i < q_ / 2; i++) {
+        const double q1 = std::exp(theta[3 + p_ + 2 * i]), q2 = std::exp(theta[3 + p_ + 2 * i + 1]);
+        const double disc = q2 * q2 - 4.0 * q1;
+        if (disc > 0) {
+            roots[2 * i] = std::complex<double>(-0.5 * (q2 + std::sqrt(disc)), 0.0);
+            roots[2 * i + 1] = std::complex<double>(-0.5 * (q2 - std::sqrt(disc)), 0.0);
+        } else {
+            roots[2 * i] = std::complex<double>(-0.5 * q2, -0.5 * std::sqrt(-disc));
+            roots[2 * i + 1] = std::conj(roots[2 * i]);
+        }
+    }
+    if (q_ % 2 == 1) roots[q_ - 1] = std::complex<double>(-std::exp(theta[3 + p_ + q_ - 1]), 0.0);
+    vecC coefs((size_t)q_ + 1, std::complex<double>(0, 0));
+    coefs[0] = 1.0;
+    for (int i = 0; i < q_; i++)
+        for (int j = i + 1; j >= 1; j--) coefs[j] = coefs[j] - roots[i] * coefs[j - 1];
+    const double norm = coefs[q_].real();
+    for (int i = 0; i <= q_; i++) ma[i] = coefs[q_ - i].real() / norm;
+    return ma;
+}
+
+vecD ZCARMA::ExtractMA(const vecD& theta) const {  // carpack.cpp:687-698
+    const double x = theta[3 + p_];
+    const double kn = std::exp(x) / (1.0 + std::exp(x));
+    const double kappa = (prior_.kappa_high - prior_.kappa_low) * kn + prior_.kappa_low;
+    vecD ma((size_t)p_, 0.0);
+    ma[0] = 1.0;
+    double binom = 1.0;
+    for (int i = 1; i < p_; i++) {
+        binom = binom * (double)(p_ - i) / (double)i;
+        ma[i] = std::rint(binom) / std::pow(kappa, (double)i);
+    }
+    return ma;
 }
 
 // ---- samplers --------------------------------------------------------------------------------

@@ -20,10 +20,10 @@
 #include <vector>
 
 #include "carma_b200.h"
+#include "carma_steps.hpp"
 
 namespace carma_host {
 
-typedef std::vector<double> vecD;
 typedef std::vector<std::vector<double> > vecvecD;
 typedef std::vector<std::complex<double> > vecC;
 
@@ -117,7 +117,9 @@ protected:
 // ------------------------------------------------------------------------------------------------
 // Model parameter classes (carpack.hpp)
 // ------------------------------------------------------------------------------------------------
-class CARMA_Base {
+// CARMA_Base<> of carpack.hpp:51-248: a Parameter<arma::vec> (parameters.hpp:96-169), so it plugs into AdaptiveMetro /
+// ExchangeStep / Sampler (carma_steps.hpp) exactly like the reference's classes.
+class CARMA_Base : public Parameter<vecD> {
 public:
     CARMA_Base(bool track, std::string name, const vecD& time, const vecD& y, const vecD& yerr, int kind, int p, int q,
                double temperature = 1.0);
@@ -126,19 +128,27 @@ public:
     int Dimension() const;
     // carpack.hpp:118-126 / 444-456
     double LogPrior(const vecD& theta) const;
-    // carpack.hpp:131-176: one LogDensity on the GPU
-    double LogDensity(const vecD& theta) const;
+    // carpack.hpp:131-176: one LogDensity on the GPU (the value is remembered for Save(), see below)
+    double LogDensity(vecD theta) override;
     // batched LogDensity: rows of theta, one kernel launch
     vecD LogDensityBatch(const vecvecD& theta) const;
     // carpack.hpp:178-191 / carpack.cpp:116-130 / 314-374, evaluated through LogDensity == -inf
-    bool CheckPriorBounds(const vecD& theta) const;
+    bool CheckPriorBounds(const vecD& theta);
+    // carpack.cpp:38-83, 175-230, 416-477, 586-644: drawn on the device until the log-density is finite; the
+    // log-density of the returned value is cached, so the Save() that follows costs no second filter run
+    vecD StartingValue() override;
+    // carpack.cpp:233-265, 479-512, 646-678
+    vecD SetStartingValue(vecD init) override;
+    // carpack.hpp:90-108: stores the value and its log-posterior.  The reference recomputes the latter from the Kalman
+    // filter left behind by the LogDensity(new_value) call that preceded it; here that call's result is cached.
+    void Save(vecD new_value) override;
+    // value + cached log-posterior in one go (used by ExchangeStep; the reference does Save + SetLogDensity)
+    void SetValue(const vecD& value, double logpost) { value_ = value; log_posterior_ = logpost; }
+    std::string StringValue() override;
     // carpack.hpp:201-207
     void SetPrior(double max_stdev) { prior_.max_stdev = max_stdev; }
     void SetKappaBounds(double lo, double hi) { prior_.kappa_low = lo; prior_.kappa_high = hi; }
     void SetMLE(bool ignore_prior) { ignore_prior_ = ignore_prior; }
-    double GetTemperature() const { return temperature_; }
-    std::string Label() const { return name_; }
-    bool Track() const { return track_; }
     vecD GetTime() const { return series_->time(); }
     vecD GetTimeSeries() const { return series_->y(); }
     vecD GetTimeSeriesErr() const { return series_->yerr(); }
@@ -150,25 +160,25 @@ public:
 
     // boost_python_wrapper.cpp:49-73 surface
     double getLogPrior(vecD theta) const { return LogPrior(theta); }
-    double getLogDensity(vecD theta) const { return LogDensity(theta); }
+    double getLogDensity(vecD theta) { return LogDensity(theta); }
     vecvecD getSamples() const { return samples_; }
-    vecD GetLogLikes() const { return logposts_; }  // parameters.hpp:160-162
 
     // filled by the samplers (parameters.hpp:136-147)
     void SetSamples(vecvecD samples, vecD logposts) { samples_ = std::move(samples); logposts_ = std::move(logposts); }
     // diagnostics of the run that produced the samples (steps.hpp:255-264, 365-370)
     vecD accept_rates, exchange_rates;
+    // Philox chain index used by StartingValue() (one per chain of a host-built ensemble)
+    void SetChainIndex(uint32_t chain) { chain_ = chain; }
 
 protected:
-    bool track_;
-    std::string name_;
-    double temperature_;
     int kind_, p_, q_;
     std::shared_ptr<DeviceSeries> series_;
     carma_prior_t prior_;
     bool ignore_prior_ = false;
-    vecvecD samples_;
-    vecD logposts_;
+    uint32_t chain_ = 0;
+    uint64_t start_draws_ = 0;
+    vecD last_theta_;        // argument of the most recent LogDensity call ...
+    double last_logpost_ = 0.0;  // ... and its value
 };
 
 class CAR1 : public CARMA_Base {
@@ -183,7 +193,12 @@ public:
         : CARMA_Base(track, name, time, y, yerr, CARMA_KIND_CARP, p, 0, temperature) {}
     // carpack.cpp:137-172 and 377-409 (host-side scalar helpers; the GPU path has its own copy)
     vecC ARRoots(const vecD& theta) const;
+    vecC ExtractAR(const vecD& theta) const { return ARRoots(theta); }  // carpack.hpp:310-313
     double Variance(const vecC& alpha_roots, const vecD& ma_coefs, double sigma, double dt = 0.0) const;
+    // carpack.hpp:314 (CARp: [1, 0, ...]); CARMA: carpack.cpp:522-580; ZCARMA: carpack.cpp:687-698
+    virtual vecD ExtractMA(const vecD& theta) const;
+    // carpack.hpp:316-319, 391-395
+    double ExtractSigsqr(const vecD& theta) const { return theta[0] * theta[0] / Variance(ARRoots(theta), ExtractMA(theta), 1.0); }
 
 protected:
     CARp(bool track, std::string name, const vecD& time, const vecD& y, const vecD& yerr, int kind, int p, int q,
@@ -201,12 +216,14 @@ class CARMA : public CARp {
 public:
     CARMA(bool track, std::string name, const vecD& time, const vecD& y, const vecD& yerr, int p, int q,
           double temperature = 1.0);
+    vecD ExtractMA(const vecD& theta) const override;
 };
 
 class ZCARMA : public CARp {
 public:
     ZCARMA(bool track, std::string name, const vecD& time, const vecD& y, const vecD& yerr, int p, double temperature = 1.0)
         : CARp(track, name, time, y, yerr, CARMA_KIND_ZCARMA, p, 0, temperature) {}
+    vecD ExtractMA(const vecD& theta) const override;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -464,6 +464,30 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
     }
 }
 
+// One starting value per thread (chains chain0 .. chain0 + n - 1), the series read from global memory: the draw
+// loop of pt_kernel on its own, for host-driven samplers (Parameter<>::StartingValue of the class API).
+template <int P>
+__global__ void start_value_kernel(SeriesView sv, PTParams pp, uint32_t chain0, int n, double* __restrict__ theta_out,
+                                   double* __restrict__ lp_out, int* __restrict__ status) {
+    MathTab tb;
+    tb.load();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double th[MAX_D];
+#pragma unroll
+    for (int j = 0; j < MAX_D; j++) th[j] = 0.0;
+    double lp = -INFINITY;
+    bool ok = false;
+    for (int a = 0; a < pp.max_start && !ok; a++) {
+        StartRng g{pp.seed, chain0 + (uint32_t)k, (uint32_t)a, 0u};
+        lp = starting_value_attempt<P>(pp, tb, g, th, sv.dt, sv.y, sv.e2n, sv.e2_0);
+        ok = isfinite(lp);
+    }
+    if (!ok) atomicExch(status, 1);
+    for (int j = 0; j < pp.d; j++) theta_out[(size_t)k * pp.d + j] = th[j];
+    lp_out[k] = lp;
+}
+
 static size_t pt_smem_bytes(int nyp, int d) {
     return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 2 * PT_BLOCK) * sizeof(double);
 }
@@ -590,6 +614,47 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         default: e = cudaErrorInvalidValue;
     }
     if (!cuda_ok(e, "pt_kernel launch")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_starting_value(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, uint64_t seed,
+                         uint32_t chain, int max_attempts, double* theta_out, double* logpost_out) {
+    if (!s || !prior || !theta_out || !logpost_out) { set_error("carma_starting_value: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model_pt(kind, p, q)) { set_error("carma_starting_value: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    PTParams pp{};
+    pp.kind = kind; pp.q = q; pp.d = model_dim(kind, p, q);
+    pp.prior = *prior;
+    pp.seed = seed; pp.max_start = std::max(1, max_attempts);
+    pp.y_mean = s->st.mean; pp.y_var_sample = s->st.var_sample; pp.y_var_pop = s->st.var_pop;
+    pp.median_dt = s->st.median_dt; pp.tspan = s->st.tmax - s->st.tmin; pp.ny = (int)s->ny;
+    pp.dt_max = s->dt_max;
+    pp.series_in_smem = 0;
+    const size_t d = (size_t)pp.d;
+    if (!s->scratch_out.reserve((d + 1) * sizeof(double) + 16)) return CARMA_ERR_CUDA;
+    double* d_th = (double*)s->scratch_out.p;
+    double* d_lp = d_th + d;
+    int* d_status = (int*)(d_lp + 1);
+    if (!cuda_ok(cudaMemset(d_status, 0, sizeof(int)), "memset status")) return CARMA_ERR_CUDA;
+    SeriesView sv = s->view();
+#define LAUNCH_SV(PP) start_value_kernel<PP><<<1, 32>>>(sv, pp, chain, 1, d_th, d_lp, d_status)
+    switch (p) {
+        case 1: LAUNCH_SV(1); break;
+        case 2: LAUNCH_SV(2); break;
+        case 3: LAUNCH_SV(3); break;
+        case 4: LAUNCH_SV(4); break;
+        case 5: LAUNCH_SV(5); break;
+        case 6: LAUNCH_SV(6); break;
+        default: LAUNCH_SV(7); break;
+    }
+#undef LAUNCH_SV
+    if (!cuda_ok(cudaGetLastError(), "start_value_kernel launch")) return CARMA_ERR_CUDA;
+    int status = 0;
+    bool ok = cuda_ok(cudaMemcpy(theta_out, d_th, d * sizeof(double), cudaMemcpyDeviceToHost), "D2H theta") &&
+              cuda_ok(cudaMemcpy(logpost_out, d_lp, sizeof(double), cudaMemcpyDeviceToHost), "D2H logpost") &&
+              cuda_ok(cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost), "D2H status");
+    if (!ok) return CARMA_ERR_CUDA;
+    if (status) { set_error("carma_starting_value: no finite starting value within max_attempts"); return CARMA_ERR_START; }
     return CARMA_OK;
 }
 

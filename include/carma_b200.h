@@ -254,6 +254,31 @@ int carma_multi_pt_run(carma_multi_series_t m, int kind, int p, int q, const car
                        const carma_pt_opts_t* opts, size_t n_ensembles, double* samples, double* logposts,
                        double* accept_rates, double* exchange_rates);
 
+/* ---- starting values ------------------------------------------------------------------------
+ * Replaces CAR1/CARp/CARMA/ZCARMA::StartingValue (src/carpack.cpp:38-83, 175-230, 416-477, 586-644): draws from the
+ * starting-value law until LogDensity is finite (at most max_attempts times), on the device, with the Philox
+ * stream (seed, chain) that carma_pt_run would use for that chain -- so a host-driven sampler built from the
+ * step classes starts exactly where the on-device sampler would.  theta_out: d values; logpost_out: its
+ * log-density.  Returns CARMA_ERR_START when no finite value was found. */
+int carma_starting_value(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, uint64_t seed,
+                         uint32_t chain, int max_attempts, double* theta_out, double* logpost_out);
+
+/* ---- multi-GPU: gather of per-rank summaries (NCCL) -----------------------------------------
+ * One process per GPU; units of work are partitioned with no data-path collective, and at the end every rank
+ * contributes `count` doubles (per-model -loglik / AICc / theta-hat, or survey moments) and receives everybody's:
+ * all[r * count + k] = local[k] of rank r.  Replaces the result return of the reference's process pool
+ * (src/carmcmc/carma_pack.py:111-119).  nccl_comm is an ncclComm_t (passed as void*): either one the host already
+ * has, or one made by carma_comm_init_rank from an id that rank 0 obtained with carma_comm_unique_id and sent to the
+ * other ranks by any means (file, socket, MPI).  NCCL is loaded at first use; without it these return CARMA_ERR_CUDA. */
+#define CARMA_COMM_ID_BYTES 128
+int carma_comm_unique_id(char id[CARMA_COMM_ID_BYTES]);
+int carma_comm_init_rank(int nranks, int rank, const char id[CARMA_COMM_ID_BYTES], int device, void** comm);
+int carma_comm_destroy(void* comm);
+int carma_gather_summaries(void* nccl_comm, const double* local, size_t count, double* all /* nranks x count */,
+                           void* stream);
+/* device-pointer variant: no copies, no synchronisation */
+int carma_gather_summaries_dev(void* nccl_comm, const double* d_local, size_t count, double* d_all, void* stream);
+
 /* ---- utilities ---------------------------------------------------------------------------- */
 /* Saturating FP64 FMA micro-benchmark on `device`: returns sustained DFMA TFLOP/s (2 flops per
  * FMA).  Used by bench.py as the measured FP64 roofline denominator. */
