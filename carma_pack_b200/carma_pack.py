@@ -12,8 +12,9 @@ purpose from the reference:
     trial) and the L-BFGS-B fits of the reference (carma_pack.py:250, finite-difference gradient) are
     replaced by a batched projected L-BFGS whose function and finite-difference gradient evaluations
     are single batched GPU launches;
-  * CarmaSample computes `loglik` with one batched launch instead of one FFI call per stored
-    sample (carma_pack.py:307-313);
+  * CarmaSample does not re-filter the stored samples to obtain `loglik` (carma_pack.py:307-313 does, one
+    FFI call per sample): with SetMLE(True) that number equals the stored log-posterior; the derived
+    quantities (roots, coefficients, sigma) are vectorised numpy;
   * Python-3 bugs of the reference are not reproduced.
 """
 import numpy as np
@@ -438,8 +439,8 @@ class CarmaSample(MCMCSample):
         time, y, ysig = np.asarray(time, float), np.asarray(y, float), np.asarray(ysig, float)
         self.time, self.y, self.ysig = time, y, ysig
         self.p, self.q = p, q
-        self._series = series if series is not None else Series(time, y, ysig)
-        self._prior = prior if prior is not None else self._series.default_prior(True)
+        self._series_obj = series      # created on first use (predict / simulate / kalman_filter): the
+        self._prior_obj = prior        # post-processing below needs no GPU
         # column names as samplers.py / carma_pack.py:286-305
         self._samples["var"] = trace[:, 0] ** 2
         self._samples["measerr_scale"] = trace[:, 1]
@@ -450,14 +451,42 @@ class CarmaSample(MCMCSample):
         self._ar_coefs()
         self._ma_coefs(trace)
         self._sigma_noise()
-        # loglik = LogDensity with SetMLE(True): one batched launch (carma_pack.py:307-313)
-        kind = KIND_CARMA if q > 0 else KIND_CARP
-        self._samples["loglik"] = self._series.loglik(kind, p, q, trace, prior=self._prior, flags=IGNORE_BOUNDS)
+        # "loglik" of the reference = getLogDensity with SetMLE(True) for every stored sample: nsamples more filter runs
+        # across the FFI (carma_pack.py:307-313).  SetMLE(True) only skips the prior-BOUNDS test; LogPrior is still added
+        # (carpack.hpp:173, 180), and every stored sample lies inside the bounds, so that number IS the stored
+        # log-posterior: nothing is re-filtered.  The pure log-likelihood (log-posterior minus LogPrior) is offered next
+        # to it as "loglik_only".
+        self._samples["loglik"] = logpost.copy()
+        self._samples["loglik_only"] = logpost - self.log_prior(trace)
         self.parameters = list(self._samples.keys())
         self.newaxis()
         self.mle = {}
         if MLE is not None:
             self.add_mle(MLE)
+
+    @property
+    def _series(self):
+        if self._series_obj is None:
+            self._series_obj = Series(self.time, self.y, self.ysig)
+        return self._series_obj
+
+    @property
+    def _prior(self):
+        if self._prior_obj is None:
+            self._prior_obj = self._series.default_prior(True)
+        return self._prior_obj
+
+    @staticmethod
+    def log_prior(trace, measerr_dof=50.0):
+        """CARMA_Base::LogPrior (carpack.hpp:118-126) for every row: the scaled inverse-chi^2 prior on measerr_scale."""
+        scale = np.asarray(trace, dtype=float)[:, 1]
+        return -0.5 * measerr_dof / scale - (1.0 + measerr_dof / 2.0) * np.log(scale)
+
+    def recompute_loglik(self):
+        """The reference's loop (carma_pack.py:307-313) as ONE batched launch: LogDensity with SetMLE(True) of every
+        stored sample.  Only needed to audit the stored log-posteriors; CarmaSample itself does not call it."""
+        kind = KIND_CARMA if self.q > 0 else KIND_CARP
+        return self._series.loglik(kind, self.p, self.q, self._trace, prior=self._prior, flags=IGNORE_BOUNDS)
 
     def _ar_roots(self):  # carma_pack.py:439-467
         qc = self._samples["quad_coefs"]
@@ -635,14 +664,32 @@ class Car1Sample(MCMCSample):
         time, y, ysig = np.asarray(time, float), np.asarray(y, float), np.asarray(ysig, float)
         self.time, self.y, self.ysig = time, y, ysig
         self.p, self.q = 1, 0
-        self._series = series if series is not None else Series(time, y, ysig)
-        self._prior = prior if prior is not None else self._series.default_prior(True)
+        self._series_obj = series
+        self._prior_obj = prior
         self._samples["var"] = trace[:, 0] ** 2
         self._samples["measerr_scale"] = trace[:, 1]
         self._samples["mu"] = trace[:, 2]
         self._samples["log_omega"] = trace[:, 3]
         omega = np.exp(trace[:, 3])
         self._samples["sigma"] = np.sqrt(2.0 * omega * trace[:, 0] ** 2)
-        self._samples["loglik"] = self._series.loglik(KIND_CAR1, 1, 0, trace, prior=self._prior)
+        # the reference's per-sample getLogDensity loop (carma_pack.py:902-905) returns the stored log-posterior again
+        self._samples["loglik"] = logpost.copy()
+        self._samples["loglik_only"] = logpost - CarmaSample.log_prior(trace)
+        self._trace = trace
         self.parameters = list(self._samples.keys())
         self.newaxis()
+
+    @property
+    def _series(self):
+        if self._series_obj is None:
+            self._series_obj = Series(self.time, self.y, self.ysig)
+        return self._series_obj
+
+    @property
+    def _prior(self):
+        if self._prior_obj is None:
+            self._prior_obj = self._series.default_prior(True)
+        return self._prior_obj
+
+    def recompute_loglik(self):
+        return self._series.loglik(KIND_CAR1, 1, 0, self._trace, prior=self._prior)

@@ -14,8 +14,9 @@
 //   1. scan_reduce_kernel : one thread per chunk of `chunk` consecutive points folds its per-point
 //      elements into one aggregate.  The right operand is always a single-point element (J_j = w w^T/S
 //      is rank one), so M comes from Sherman-Morrison: no matrix inverse in this pass.
-//   2. scan_prefix_kernel : one block scans the aggregates (general operator, Gauss-Jordan inverse with
-//      partial pivoting on a PxP matrix) and emits the filtered state in front of every chunk.
+//   2. scan_block / scan_totals / scan_apply kernels : a two-level Kogge-Stone scan of the aggregates over many
+//      blocks (general operator, Gauss-Jordan inverse with partial pivoting on a PxP matrix) that emits the
+//      filtered state in front of every chunk.
 //   3. scan_filter_kernel : one thread per chunk re-runs the ordinary sequential filter (KalmanReal,
 //      the same code as K1) from that state and sums its chunk's log-likelihood terms.
 //   4. scan_sum_kernel    : fixed-order reduction of the chunk sums (+ log-prior): deterministic.
@@ -353,60 +354,109 @@ scan_reduce_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chu
     E[m] = acc;
 }
 
-// pass 2: one block.  T threads, thread t owns aggregates [t*R, min((t+1)*R, M)).
+// pass 2, hierarchical (round 1 ran it in ONE block: 61 % of the whole evaluation at ny = 10^6):
+//   2a  scan_block_kernel    every block of 256 aggregates does a Kogge-Stone inclusive scan (8 combine levels, operands
+//                            exchanged through an L2-resident double buffer) -> within-block prefixes I[m], block totals;
+//   2b  scan_totals_kernel   one block scans the <= 256 block totals the same way -> filtered state at every block start;
+//   2c  scan_apply_kernel    every aggregate pushes its block's start state through its within-block prefix: the
+//                            filtered state in front of chunk m + 1.
+// Sequential depth: 8 + 8 + 1 combines instead of ~70.
+constexpr int SCAN_TILE = 256;
+
 template <int P>
-__global__ void __launch_bounds__(256)
-scan_prefix_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ E, int M, int R, int T,
-                   ScanElem<P>* __restrict__ X /* 2*T */, FiltState<P>* __restrict__ F /* M */) {
-    spp += blockIdx.x;  // one block per theta row
-    E += (size_t)blockIdx.x * M;
-    X += (size_t)blockIdx.x * 2 * T;
-    F += (size_t)blockIdx.x * M;
-    if (spp->status != TT_OK) return;
-    const int t = threadIdx.x;
-    const int lo = t * R, hi = min(M, lo + R);
-    const bool have = t < T && lo < M;
-    if (have) {
-        ScanElem<P> acc = E[lo], tmp;
-        for (int m = lo + 1; m < hi; m++) {
-            combine<P>(acc, E[m], tmp);
-            acc = tmp;
-        }
-        X[t] = acc;
-    }
-    __syncthreads();
-    // Hillis-Steele inclusive scan over X[0..T), double buffered in global memory
-    int src = 0;
-    for (int off = 1; off < T; off <<= 1) {
+__global__ void __launch_bounds__(SCAN_TILE)
+scan_block_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ E, int M, int nblk,
+                  ScanElem<P>* __restrict__ X /* 2 M per row */, ScanElem<P>* __restrict__ I /* M per row */,
+                  ScanElem<P>* __restrict__ B /* nblk per row */) {
+    const int row = blockIdx.y;
+    if (spp[row].status != TT_OK) return;
+    E += (size_t)row * M;
+    X += (size_t)row * 2 * M;
+    I += (size_t)row * M;
+    B += (size_t)row * nblk;
+    const int t = threadIdx.x, m = blockIdx.x * SCAN_TILE + t;
+    const bool have = m < M;
+    ScanElem<P> acc;
+    if (have) acc = E[m];
+    const ScanElem<P>* prev = E;
+    int lvl = 0;
+    for (int off = 1; off < SCAN_TILE; off <<= 1, lvl++) {
+        ScanElem<P>* next = X + (size_t)(lvl & 1) * M;
         if (have) {
             if (t >= off) {
                 ScanElem<P> out;
-                combine<P>(X[src * T + t - off], X[src * T + t], out);
-                X[(1 - src) * T + t] = out;
-            } else {
-                X[(1 - src) * T + t] = X[src * T + t];
+                combine<P>(prev[m - off], acc, out);
+                acc = out;
             }
+            next[m] = acc;
         }
-        src = 1 - src;
+        prev = next;
         __threadfence_block();
         __syncthreads();
     }
     if (have) {
-        FiltState<P> f;
-        int start = lo;
-        if (t == 0) {
-            // chunk 0 has no predecessor; the state in front of chunk 1 is the first aggregate itself
-            for (int i = 0; i < P; i++) { f.b[i] = E[0].b[i]; for (int j = 0; j < P; j++) f.C[i][j] = E[0].C[i][j]; }
-            start = 1;
-        } else {
-            const ScanElem<P>& pre = X[src * T + t - 1];  // inclusive prefix of everything before this run
-            for (int i = 0; i < P; i++) { f.b[i] = pre.b[i]; for (int j = 0; j < P; j++) f.C[i][j] = pre.C[i][j]; }
-        }
-        for (int m = start; m < hi; m++) {
-            F[m] = f;
-            if (m + 1 < hi) apply_elem<P>(f, E[m]);
-        }
+        I[m] = acc;
+        if (t == SCAN_TILE - 1 || m == M - 1) B[blockIdx.x] = acc;
     }
+}
+
+template <int P>
+__global__ void __launch_bounds__(SCAN_TILE)
+scan_totals_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ B, int nblk,
+                   ScanElem<P>* __restrict__ BX /* 2 nblk per row */, FiltState<P>* __restrict__ S /* nblk per row */) {
+    const int row = blockIdx.x;
+    if (spp[row].status != TT_OK) return;
+    B += (size_t)row * nblk;
+    BX += (size_t)row * 2 * nblk;
+    S += (size_t)row * nblk;
+    const int t = threadIdx.x;
+    const bool have = t < nblk;
+    ScanElem<P> acc;
+    if (have) acc = B[t];
+    const ScanElem<P>* prev = B;
+    int lvl = 0;
+    for (int off = 1; off < nblk; off <<= 1, lvl++) {
+        ScanElem<P>* next = BX + (size_t)(lvl & 1) * nblk;
+        if (have) {
+            if (t >= off) {
+                ScanElem<P> out;
+                combine<P>(prev[t - off], acc, out);
+                acc = out;
+            }
+            next[t] = acc;
+        }
+        prev = next;
+        __threadfence_block();
+        __syncthreads();
+    }
+    // state at the START of block t + 1 = (b, C) of the inclusive prefix over blocks 0..t
+    if (have && t + 1 < nblk) {
+        FiltState<P> f;
+        for (int i = 0; i < P; i++) { f.b[i] = acc.b[i]; for (int j = 0; j < P; j++) f.C[i][j] = acc.C[i][j]; }
+        S[t + 1] = f;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(SCAN_TILE)
+scan_apply_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __restrict__ I, const FiltState<P>* __restrict__ S,
+                  int M, int nblk, FiltState<P>* __restrict__ F /* M per row */) {
+    const int row = blockIdx.y;
+    if (spp[row].status != TT_OK) return;
+    I += (size_t)row * M;
+    S += (size_t)row * nblk;
+    F += (size_t)row * M;
+    const int m = blockIdx.x * SCAN_TILE + threadIdx.x;
+    if (m + 1 >= M) return;  // F[m + 1] is the state in front of chunk m + 1; chunk 0 starts from Reset()
+    FiltState<P> f;
+    if (blockIdx.x == 0) {
+        // no predecessor block: the prefix itself carries the filtered state (its first element is the prior update)
+        for (int i = 0; i < P; i++) { f.b[i] = I[m].b[i]; for (int j = 0; j < P; j++) f.C[i][j] = I[m].C[i][j]; }
+    } else {
+        f = S[blockIdx.x];
+        apply_elem<P>(f, I[m]);
+    }
+    F[m + 1] = f;
 }
 
 // pass 3
@@ -487,27 +537,38 @@ static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const car
     const int d = model_dim(kind, P, q);
     if (chunk <= 0) chunk = 128;
     chunk = std::max(chunk, 2);
+    // two scan levels of 256 cover 65,536 aggregates: longer series get longer chunks
+    chunk = std::max(chunk, (int)((sv.ny + (SCAN_TILE * SCAN_TILE) - 1) / (SCAN_TILE * SCAN_TILE)));
     const int M = (sv.ny + chunk - 1) / chunk;
-    int T = std::min(256, M);
-    const int R = (M + T - 1) / T;
-    T = (M + R - 1) / R;
+    const int nblk = (M + SCAN_TILE - 1) / SCAN_TILE;
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_sp = align((size_t)nrows * sizeof(ScanParams<P>));
     const size_t b_E = align((size_t)nrows * M * sizeof(ScanElem<P>));
-    const size_t b_X = align((size_t)nrows * 2 * T * sizeof(ScanElem<P>));
+    const size_t b_X = align((size_t)nrows * 2 * M * sizeof(ScanElem<P>));
+    const size_t b_I = align((size_t)nrows * M * sizeof(ScanElem<P>));
+    const size_t b_B = align((size_t)nrows * nblk * sizeof(ScanElem<P>));
+    const size_t b_BX = align((size_t)nrows * 2 * nblk * sizeof(ScanElem<P>));
+    const size_t b_S = align((size_t)nrows * nblk * sizeof(FiltState<P>));
     const size_t b_F = align((size_t)nrows * M * sizeof(FiltState<P>));
     const size_t b_LL = align((size_t)nrows * M * sizeof(double));
-    if (!s->scratch_misc.reserve(b_sp + b_E + b_X + b_F + b_LL + 256)) return CARMA_ERR_CUDA;
+    if (!s->scratch_misc.reserve(b_sp + b_E + b_X + b_I + b_B + b_BX + b_S + b_F + b_LL + 256)) return CARMA_ERR_CUDA;
     char* base = (char*)s->scratch_misc.p;
-    ScanParams<P>* sp = (ScanParams<P>*)base;
-    ScanElem<P>* E = (ScanElem<P>*)(base + b_sp);
-    ScanElem<P>* X = (ScanElem<P>*)(base + b_sp + b_E);
-    FiltState<P>* F = (FiltState<P>*)(base + b_sp + b_E + b_X);
-    double* LL = (double*)(base + b_sp + b_E + b_X + b_F);
+    ScanParams<P>* sp = (ScanParams<P>*)base; base += b_sp;
+    ScanElem<P>* E = (ScanElem<P>*)base; base += b_E;
+    ScanElem<P>* X = (ScanElem<P>*)base; base += b_X;
+    ScanElem<P>* I = (ScanElem<P>*)base; base += b_I;
+    ScanElem<P>* B = (ScanElem<P>*)base; base += b_B;
+    ScanElem<P>* BX = (ScanElem<P>*)base; base += b_BX;
+    FiltState<P>* S = (FiltState<P>*)base; base += b_S;
+    FiltState<P>* F = (FiltState<P>*)base; base += b_F;
+    double* LL = (double*)base;
     scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, sv.dt_max, d_theta, sp, nrows);
     dim3 grid((unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK), (unsigned)nrows);
+    dim3 tgrid((unsigned)nblk, (unsigned)nrows);
     scan_reduce_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, E);
-    scan_prefix_kernel<P><<<nrows, 256, 0, st>>>(sp, E, M, R, T, X, F);
+    scan_block_kernel<P><<<tgrid, SCAN_TILE, 0, st>>>(sp, E, M, nblk, X, I, B);
+    scan_totals_kernel<P><<<nrows, SCAN_TILE, 0, st>>>(sp, B, nblk, BX, S);
+    scan_apply_kernel<P><<<tgrid, SCAN_TILE, 0, st>>>(sp, I, S, M, nblk, F);
     scan_filter_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL);
     scan_sum_kernel<P><<<nrows, 256, 0, st>>>(sp, LL, M, d_out);
     return cuda_ok(cudaGetLastError(), "scan kernels launch") ? CARMA_OK : CARMA_ERR_CUDA;
@@ -532,7 +593,7 @@ int carma_loglik_scan_dev(carma_series_t s, int kind, int p, int q, const carma_
     cudaStream_t st = (cudaStream_t)stream;
     // rows are processed in groups so that the per-row scratch stays below ~1 GiB (and grid.y <= 65535)
     const size_t chunk_eff = chunk > 0 ? (size_t)std::max(chunk, 2) : 128;
-    size_t per_row = ((size_t)s->ny / chunk_eff + 2) * (size_t)(4 * p * p + 3 * p + 1) * sizeof(double) * 2;
+    size_t per_row = ((size_t)s->ny / chunk_eff + 2) * (size_t)(4 * p * p + 3 * p + 1) * sizeof(double) * 5;
     size_t group = std::max<size_t>(1, std::min<size_t>(n, std::min<size_t>(4096, ((size_t)1 << 30) / std::max<size_t>(per_row, 1))));
     for (size_t i0 = 0; i0 < n; i0 += group) {
         const int nr = (int)std::min(group, n - i0);

@@ -270,6 +270,18 @@ def make_loglik_fixture():
     np.savez(os.path.join(HERE, "loglik_cases.npz"), **flat)
 
 
+def make_derived_fixture():
+    """Posterior post-processing of CarmaSample (src/carmcmc/carma_pack.py:439-546: _ar_roots, _ma_coefs, _sigma_noise,
+    run unchanged) on the theta rows of loglik_cases.npz: AR roots, MA coefficients and sigma^2 per row."""
+    cases = dict(np.load(os.path.join(HERE, "loglik_cases.npz")))
+    out = {}
+    for name in sorted({k.split("_")[0] for k in cases if k.startswith("c") and k.endswith("_theta")}):
+        p, q = int(cases[name + "_p"]), int(cases[name + "_q"])
+        roots, ma, sigsqr = theta_to_params(cases[name + "_theta"], p, q)
+        out[name + "_roots"], out[name + "_ma"], out[name + "_sigsqr"] = roots, ma, np.ravel(sigsqr)
+    np.savez_compressed(os.path.join(HERE, "derived_params.npz"), **out)
+
+
 def make_mcmc_fixtures():
     """The reference's own 1000-point test series for the long statistical tests (posterior recovery within 3 sigma,
     residual whiteness): cpp_tests/data/{car5,zcar5,carma}_test.dat with the true parameters of
@@ -325,3 +337,4 @@ if __name__ == "__main__":
     make_loglik_fixture()
     make_car1_fixture()
     make_mcmc_fixtures()
+    make_derived_fixture()
