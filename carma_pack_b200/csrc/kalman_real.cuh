@@ -99,6 +99,12 @@ struct KalmanReal {
     CARMA_HD void predict_observe(const RealParams<P>& prm, const Tab& tb, double dt, double e2n) {
         double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
         transition<ALLC>(prm, tb, dt, fa, fb, fsb, &fo);
+        propagate(prm, fa, fb, fsb, fo, e2n);
+    }
+
+    // state / covariance prediction with given transition blocks, then the predicted observation
+    CARMA_HD void propagate(const RealParams<P>& prm, const double* fa, const double* fb, const double* fsb, double fo,
+                            double e2n) {
 
         // ---- predict state
 #pragma unroll

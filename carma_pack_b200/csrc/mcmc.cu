@@ -26,6 +26,7 @@
 // evaluation order does not matter.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
