@@ -102,6 +102,38 @@ struct KalmanReal {
         propagate(prm, fa, fb, fsb, fo, e2n);
     }
 
+    // v <- Phi v for an extra state-like vector (Predict's linear coefficients, kfilter.cpp:290-337)
+    static CARMA_HD void propagate_vec(const double* fa, const double* fb, const double* fsb, double fo, double* v) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const double u = v[2 * s], w = v[2 * s + 1];
+            v[2 * s] = fma(fa[s], u, fsb[s] * w);
+            v[2 * s + 1] = fma(fb[s], u, fa[s] * w);
+        }
+        if (ODD) v[P - 1] *= fo;
+    }
+    // c . v with the observation row c = (1,0,1,0,...[,1])
+    static CARMA_HD double observe_vec(const double* v) {
+        double m = v[0];
+#pragma unroll
+        for (int i = 2; i < P; i++)
+            if ((i & 1) == 0) m += v[i];
+        return m;
+    }
+    // g = D c + h, var = c.g + scale e2, mean = c.z for the CURRENT (z, D): what predict_observe ends with
+    CARMA_HD void observe(const RealParams<P>& prm, double e2) {
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+            double acc = prm.h[i];
+#pragma unroll
+            for (int j = 0; j < P; j++)
+                if ((j & 1) == 0) acc += D[(i <= j) ? idx(i, j) : idx(j, i)];
+            g[i] = acc;
+        }
+        var = fma(prm.scale, e2, observe_vec(g));
+        mean = observe_vec(z);
+    }
+
     // state / covariance prediction with given transition blocks, then the predicted observation
     CARMA_HD void propagate(const RealParams<P>& prm, const double* fa, const double* fb, const double* fsb, double fo,
                             double e2n) {

@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <limits>
 #include <type_traits>
+#include <utility>
+#include <vector>
 
 #include "kalman_real.cuh"
 #include "series.h"
@@ -302,6 +304,127 @@ __global__ void predict_kernel(SeriesView sv, FilterArgs a, const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Predict in the real-half recursion, resuming from stored forward states (explicit models whose roots are closed
+// under conjugation -- every model the theta parameterisation can produce).  The forward filter runs ONCE (time-parallel,
+// scan.cu) and leaves the state predicted at every data point; a query thread loads the state in front of its
+// insertion point and runs only the linear-coefficient pass over the points behind it (kfilter.cpp:252-281).
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(64)
+predict_real_kernel(SeriesView sv, ExplicitModel ex, const double* __restrict__ state, const double* __restrict__ tq, size_t nq,
+                    double* __restrict__ qmean, double* __restrict__ qvar) {
+    constexpr int NS = P / 2, NT = P * (P + 1) / 2, SD = P + NT;
+    MathTab tb;
+    tb.load();
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nq) return;
+    RealParams<P> prm;
+    if (explicit_constants<P>(ex, sv.dt_max, prm) != TT_OK) { qmean[k] = NAN; qvar[k] = NAN; return; }
+    const double time = tq[k];
+    const int ny = sv.ny;
+    int lo = 0, hi = ny;  // ip = number of data times strictly before `time` (kfilter.cpp:223-229)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sv.t[mid] < time) lo = mid + 1; else hi = mid;
+    }
+    const int ip = lo;
+    auto e2_at = [&](int i) { return i == 0 ? sv.e2_0 : sv.e2n[i - 1]; };
+    KalmanReal<P> kf;
+    double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
+    double pmean, pvar;
+    if (ip == 0) {
+        kf.reset(prm, 0.0);       // stationary law: mean 0, variance Re(b V b^H), g = V b^H
+        pmean = 0.0;
+        pvar = prm.v0;
+    } else {
+        const double* st = state + (size_t)(ip - 1) * SD;
+#pragma unroll
+        for (int i = 0; i < P; i++) kf.z[i] = st[i];
+#pragma unroll
+        for (int i = 0; i < NT; i++) kf.D[i] = st[P + i];
+        kf.observe(prm, e2_at(ip - 1));
+        const double innov = (sv.y[ip - 1] - prm.mu) - kf.mean;
+        kf.template advance<false>(prm, tb, innov, 1.0 / kf.var, fabs(time - sv.t[ip - 1]), 0.0);  // no noise at t*
+        pmean = kf.mean;
+        pvar = kf.var;
+    }
+    if (ip == ny) { qmean[k] = pmean; qvar[k] = pvar; return; }   // forecast: nothing behind the query
+    // InitializeCoefs (kfilter.cpp:290-312): y* enters as a noiseless pseudo-observation with the predictive law
+    double prec = 1.0 / pvar, pm = pmean * prec;
+    double zs[P];
+    {
+        const double inv = 1.0 / pvar;
+#pragma unroll
+        for (int i = 0; i < P; i++) zs[i] = kf.g[i] * inv;            // state_slope = K
+        kf.measurement_update(-pmean, inv);                           // state_const = x - K ymean ; P -= yvar K K^H
+        KalmanReal<P>::template transition<false>(prm, tb, fabs(sv.t[ip] - time), fa, fb, fsb, &fo);
+        KalmanReal<P>::propagate_vec(fa, fb, fsb, fo, zs);
+        kf.propagate(prm, fa, fb, fsb, fo, e2_at(ip));                // kf.mean = yconst, kf.var = var[ip]
+    }
+    double yslope = KalmanReal<P>::observe_vec(zs);
+    prec += yslope * yslope / kf.var;
+    pm += yslope * ((sv.y[ip] - prm.mu) - kf.mean) / kf.var;
+    for (int i = ip + 1; i < ny; i++) {                               // UpdateCoefs (kfilter.cpp:316-337)
+        const double inv = 1.0 / kf.var;
+        const double sl = yslope * inv;
+#pragma unroll
+        for (int j = 0; j < P; j++) zs[j] = fma(-kf.g[j], sl, zs[j]);  // state_slope -= K yslope
+        kf.measurement_update((sv.y[i - 1] - prm.mu) - kf.mean, inv);  // state_const += K (y - yconst) ; P -= var K K^H
+        KalmanReal<P>::template transition<false>(prm, tb, sv.dt[i - 1], fa, fb, fsb, &fo);
+        KalmanReal<P>::propagate_vec(fa, fb, fsb, fo, zs);
+        kf.propagate(prm, fa, fb, fsb, fo, e2_at(i));
+        yslope = KalmanReal<P>::observe_vec(zs);
+        prec += yslope * yslope / kf.var;
+        pm += yslope * ((sv.y[i] - prm.mu) - kf.mean) / kf.var;
+    }
+    pvar = 1.0 / prec;
+    qmean[k] = pm * pvar;
+    qvar[k] = pvar;
+}
+
+bool arrange_roots(const double* om, const double* ma, int p, double sigsqr, double scale, double mu, ExplicitModel* out) {
+    if (p < 1 || p > MAX_P) return false;
+    std::vector<int> reals, used(p, 0);
+    std::vector<std::pair<int, int> > pairs;
+    for (int i = 0; i < p; i++) {
+        if (used[i]) continue;
+        const double re = om[2 * i], im = om[2 * i + 1];
+        if (!std::isfinite(re) || !std::isfinite(im)) return false;
+        if (im == 0.0) { reals.push_back(i); used[i] = 1; continue; }
+        int partner = -1;
+        const double mag = std::hypot(re, im);
+        for (int j = i + 1; j < p; j++) {
+            if (used[j]) continue;
+            if (std::fabs(om[2 * j] - re) <= 1e-13 * mag && std::fabs(om[2 * j + 1] + im) <= 1e-13 * mag) { partner = j; break; }
+        }
+        if (partner < 0) return false;
+        used[i] = used[partner] = 1;
+        pairs.push_back(im < 0 ? std::make_pair(i, partner) : std::make_pair(partner, i));  // first root: Im <= 0
+    }
+    if ((reals.size() & 1u) != (size_t)(p & 1)) return false;
+    std::sort(reals.begin(), reals.end(), [&](int a, int b) { return om[2 * a] < om[2 * b]; });
+    ExplicitModel ex{};
+    ex.sigsqr = sigsqr; ex.scale = scale; ex.mu = mu; ex.cmask = 0;
+    int slot = 0;
+    for (auto& pr : pairs) {
+        ex.w_re[2 * slot] = om[2 * pr.first]; ex.w_im[2 * slot] = om[2 * pr.first + 1];
+        ex.w_re[2 * slot + 1] = om[2 * pr.first]; ex.w_im[2 * slot + 1] = -om[2 * pr.first + 1];   // the exact conjugate
+        ex.cmask |= 1u << slot;
+        slot++;
+    }
+    size_t r = 0;
+    for (; r + 1 < reals.size(); r += 2, slot++) {   // two real roots per slot, the more negative one first
+        ex.w_re[2 * slot] = om[2 * reals[r]]; ex.w_im[2 * slot] = 0.0;
+        ex.w_re[2 * slot + 1] = om[2 * reals[r + 1]]; ex.w_im[2 * slot + 1] = 0.0;
+        if (ex.w_re[2 * slot] == ex.w_re[2 * slot + 1]) return false;  // repeated root: singular Vandermonde
+    }
+    if (p & 1) { ex.w_re[p - 1] = om[2 * reals[r]]; ex.w_im[p - 1] = 0.0; }
+    for (int i = 0; i < MAX_P; i++) ex.ma[i] = i < p ? ma[i] : 0.0;
+    *out = ex;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 FMA saturation micro-benchmark (roofline denominator measured on the same GPU)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
@@ -464,7 +587,7 @@ int carma_series_destroy(carma_series_t s) {
     if (!s) return CARMA_OK;
     cudaSetDevice(s->device);
     if (s->d_pack) cudaFree(s->d_pack);
-    s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release();
+    s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release(); s->scratch_state.release();
     for (int k = 0; k < 2; k++) {
         s->slot_in[k].release(); s->slot_out[k].release();
         if (s->slot_stream[k]) cudaStreamDestroy(s->slot_stream[k]);
@@ -671,6 +794,22 @@ int carma_filter(carma_series_t s, double sigsqr, const double* omega_reim, cons
     double* d_mean = (double*)s->scratch_out.p;
     double* d_var = d_mean + ny;
     int* d_status = (int*)(d_var + ny);
+    // roots closed under conjugation (every physical model): the time-parallel real-half filter (scan.cu) writes
+    // mean / var of all points; otherwise the general complex recursion on one thread
+    ExplicitModel ex;
+    const char* env_general = getenv("CARMA_PREDICT_GENERAL");
+    if (!(env_general && env_general[0] == '1') && arrange_roots(omega_reim, ma, p, sigsqr, measerr_scale, mu, &ex)) {
+        double* d_ll = (double*)d_status;
+        int rc2 = scan_explicit(s, p, ex, d_mean, d_var, nullptr, d_ll, 0);
+        if (rc2) return rc2;
+        double ll = 0.0;
+        if (!cuda_ok(cudaMemcpy(&ll, d_ll, sizeof(double), cudaMemcpyDeviceToHost), "D2H loglik")) return CARMA_ERR_CUDA;
+        if (std::isfinite(ll) || std::isnan(ll)) {   // -inf = the constants could not be formed: let the complex path report it
+            if (!cuda_ok(cudaMemcpy(mean, d_mean, ny * sizeof(double), cudaMemcpyDeviceToHost), "D2H mean")) return CARMA_ERR_CUDA;
+            if (!cuda_ok(cudaMemcpy(var, d_var, ny * sizeof(double), cudaMemcpyDeviceToHost), "D2H var")) return CARMA_ERR_CUDA;
+            return CARMA_OK;
+        }
+    }
     filter_kernel<<<1, 32>>>(s->view(), a, d_mean, d_var, d_status);
     if (!cuda_ok(cudaGetLastError(), "filter_kernel launch")) return CARMA_ERR_CUDA;
     int status = 0;
@@ -700,6 +839,41 @@ int carma_predict(carma_series_t s, double sigsqr, const double* omega_reim, con
     int* d_status = (int*)(d_v + nq);
     if (!cuda_ok(cudaMemset(d_status, 0, sizeof(int)), "memset status")) return CARMA_ERR_CUDA;
     if (!cuda_ok(cudaMemcpy(d_tq, tq, nq * sizeof(double), cudaMemcpyHostToDevice), "H2D tq")) return CARMA_ERR_CUDA;
+    // fast path: one time-parallel forward filter leaves the predicted state at every data point; every query resumes
+    // from the state in front of it (real-half recursion).  Needs conjugate-symmetric roots and room for the states.
+    ExplicitModel ex;
+    const size_t state_doubles = (size_t)s->ny * (size_t)(p + p * (p + 1) / 2);
+    const char* env_general = getenv("CARMA_PREDICT_GENERAL");   // "1": force the general complex kernel (tests, timing)
+    const bool force_general = env_general && env_general[0] == '1';
+    if (!force_general && state_doubles * sizeof(double) <= ((size_t)1 << 30) &&
+        arrange_roots(omega_reim, ma, p, sigsqr, measerr_scale, mu, &ex)) {
+        if (!s->scratch_state.reserve((state_doubles + 2) * sizeof(double))) return CARMA_ERR_CUDA;
+        double* d_state = (double*)s->scratch_state.p;
+        double* d_ll = d_state + state_doubles;
+        int rc2 = scan_explicit(s, p, ex, nullptr, nullptr, d_state, d_ll, 0);
+        if (rc2) return rc2;
+        double ll = 0.0;
+        if (!cuda_ok(cudaMemcpy(&ll, d_ll, sizeof(double), cudaMemcpyDeviceToHost), "D2H loglik")) return CARMA_ERR_CUDA;
+        if (std::isfinite(ll) || std::isnan(ll)) {
+            const unsigned g64 = (unsigned)((nq + 63) / 64);
+            SeriesView sv = s->view();
+#define LAUNCH_PR(PP) predict_real_kernel<PP><<<g64, 64>>>(sv, ex, d_state, d_tq, nq, d_m, d_v)
+            switch (p) {
+                case 1: LAUNCH_PR(1); break;
+                case 2: LAUNCH_PR(2); break;
+                case 3: LAUNCH_PR(3); break;
+                case 4: LAUNCH_PR(4); break;
+                case 5: LAUNCH_PR(5); break;
+                case 6: LAUNCH_PR(6); break;
+                default: LAUNCH_PR(7); break;
+            }
+#undef LAUNCH_PR
+            if (!cuda_ok(cudaGetLastError(), "predict_real_kernel launch")) return CARMA_ERR_CUDA;
+            if (!cuda_ok(cudaMemcpy(qmean, d_m, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qmean")) return CARMA_ERR_CUDA;
+            if (!cuda_ok(cudaMemcpy(qvar, d_v, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qvar")) return CARMA_ERR_CUDA;
+            return CARMA_OK;
+        }
+    }
     unsigned grid = (unsigned)((nq + 31) / 32);
     predict_kernel<<<grid, 32>>>(s->view(), a, d_tq, nq, d_m, d_v, d_status);
     if (!cuda_ok(cudaGetLastError(), "predict_kernel launch")) return CARMA_ERR_CUDA;

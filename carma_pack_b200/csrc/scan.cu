@@ -64,6 +64,20 @@ __global__ void scan_params_kernel(int kind, int q, int d, unsigned flags, carma
         for (int n = m; n < P; n++) { out->V[m][n] = Vr[o]; out->V[n][m] = Vr[o]; o++; }
 }
 
+// the same for a model given by (sigsqr, omega, ma): the KalmanFilterp class API
+template <int P>
+__global__ void scan_params_explicit_kernel(ExplicitModel ex, double dt_max, ScanParams<P>* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double Vr[P * (P + 1) / 2];
+    RealParams<P> prm;
+    int st = explicit_constants<P, true>(ex, dt_max, prm, Vr);
+    out->status = st;
+    out->prm = prm;
+    int o = 0;
+    for (int m = 0; m < P; m++)
+        for (int n = m; n < P; n++) { out->V[m][n] = Vr[o]; out->V[n][m] = Vr[o]; o++; }
+}
+
 // dense transition matrix Phi(dt) in the real basis: 2x2 blocks [[A, sB],[B, A]] (kalman_real.cuh)
 template <int P>
 __device__ void build_phi(const RealParams<P>& prm, const MathTab& tb, double dt, double F[P][P]) {
@@ -459,11 +473,22 @@ scan_apply_kernel(const ScanParams<P>* __restrict__ spp, const ScanElem<P>* __re
     F[m + 1] = f;
 }
 
-// pass 3
+// What pass 3 can write per point besides the log-likelihood terms: the one-step predictive mean / variance
+// (KalmanFilter<>::mean, var: kfilter.hpp:31-32) and the whole predicted state (z, D) -- the latter is what Predict
+// resumes from, so that no query re-runs the filter over the points in front of it.
 template <int P>
+struct ScanEmit {
+    double* mean;   // [ny] or nullptr
+    double* var;    // [ny] or nullptr
+    double* state;  // [ny][STATE_DOUBLES] or nullptr: z[P], D[NT] of the state predicted at point i (before conditioning on it)
+    static constexpr int STATE_DOUBLES = P + P * (P + 1) / 2;
+};
+
+// pass 3
+template <int P, bool EMIT>
 __global__ void __launch_bounds__(SCAN_BLOCK)
 scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chunk, int nchunks,
-                   const FiltState<P>* __restrict__ F, double* __restrict__ LL) {
+                   const FiltState<P>* __restrict__ F, double* __restrict__ LL, ScanEmit<P> em) {
     MathTab tb;
     tb.load();
     spp += blockIdx.y;
@@ -489,9 +514,30 @@ scan_filter_kernel(SeriesView sv, const ScanParams<P>* __restrict__ spp, int chu
         kf.template predict_observe<false>(prm, tb, sv.dt[lo - 1], sv.e2n[lo - 1]);
     }
     const int len = hi - lo;
+    const SeriesPtr src{sv.dt + lo, sv.y + lo, sv.e2n + lo};
+    if (EMIT) {
+        // explicit per-point loop (row 0 only: emission is a single-model operation)
+        double ll = 0.0;
+        for (int i = 0; i < len; i++) {
+            const int gi = lo + i;
+            if (em.mean) em.mean[gi] = kf.mean;
+            if (em.var) em.var[gi] = kf.var;
+            if (em.state) {
+                double* st = em.state + (size_t)gi * ScanEmit<P>::STATE_DOUBLES;
+#pragma unroll
+                for (int k = 0; k < P; k++) st[k] = kf.z[k];
+#pragma unroll
+                for (int k = 0; k < KalmanReal<P>::NT; k++) st[P + k] = kf.D[k];
+            }
+            const double innov = (src.y[i] - prm.mu) - kf.mean;
+            ll += -0.5 * log(kf.var) - 0.5 * innov * innov / kf.var;
+            if (gi + 1 < sv.ny) kf.template advance<false>(prm, tb, innov, 1.0 / kf.var, src.dt[i], src.e[i]);
+        }
+        LL[m] = ll;
+        return;
+    }
     // every point of the chunk is scored; the transition out of the last one belongs to the next chunk
     const KalmanReal<P> kf0 = kf;
-    const SeriesPtr src{sv.dt + lo, sv.y + lo, sv.e2n + lo};
     filter_span_impl<P, false, true>(kf, acc, prm, tb, src, len, len - 1);
     double ll = acc.value();
     if (acc.bad()) {  // a variance outside the normal range: redo the chunk with one log() per point
@@ -529,12 +575,12 @@ scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict_
     if (threadIdx.x == 0) *out = sh[0] + spp->prm.logprior;
 }
 
-// nrows theta rows on one series: 5 launches in total (grid.y / one block per row)
-template <int P>
-static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const carma_prior_t& prior, const double* d_theta,
-                     double* d_out, int nrows, int chunk, cudaStream_t st) {
+// The scan passes for `nrows` models whose ScanParams are produced by `fill_params(sp)`; with `em` (nrows must be 1)
+// pass 3 also writes the per-point predictive mean / variance / state.
+template <int P, class FillParams>
+static int scan_core(carma_series* s, int nrows, int chunk, cudaStream_t st, double* d_out, const ScanEmit<P>* em,
+                     FillParams fill_params) {
     SeriesView sv = s->view();
-    const int d = model_dim(kind, P, q);
     if (chunk <= 0) chunk = 128;
     chunk = std::max(chunk, 2);
     // two scan levels of 256 cover 65,536 aggregates: longer series get longer chunks
@@ -562,16 +608,54 @@ static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const car
     FiltState<P>* S = (FiltState<P>*)base; base += b_S;
     FiltState<P>* F = (FiltState<P>*)base; base += b_F;
     double* LL = (double*)base;
-    scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, sv.dt_max, d_theta, sp, nrows);
+    fill_params(sp);
     dim3 grid((unsigned)((M + SCAN_BLOCK - 1) / SCAN_BLOCK), (unsigned)nrows);
     dim3 tgrid((unsigned)nblk, (unsigned)nrows);
     scan_reduce_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, E);
     scan_block_kernel<P><<<tgrid, SCAN_TILE, 0, st>>>(sp, E, M, nblk, X, I, B);
     scan_totals_kernel<P><<<nrows, SCAN_TILE, 0, st>>>(sp, B, nblk, BX, S);
     scan_apply_kernel<P><<<tgrid, SCAN_TILE, 0, st>>>(sp, I, S, M, nblk, F);
-    scan_filter_kernel<P><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL);
+    if (em) scan_filter_kernel<P, true><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL, *em);
+    else scan_filter_kernel<P, false><<<grid, SCAN_BLOCK, 0, st>>>(sv, sp, chunk, M, F, LL, ScanEmit<P>{nullptr, nullptr, nullptr});
     scan_sum_kernel<P><<<nrows, 256, 0, st>>>(sp, LL, M, d_out);
     return cuda_ok(cudaGetLastError(), "scan kernels launch") ? CARMA_OK : CARMA_ERR_CUDA;
+}
+
+// nrows theta rows on one series: 7 launches in total (grid.y / one block per row)
+template <int P>
+static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const carma_prior_t& prior, const double* d_theta,
+                     double* d_out, int nrows, int chunk, cudaStream_t st) {
+    const int d = model_dim(kind, P, q);
+    const double dt_max = s->dt_max;
+    return scan_core<P>(s, nrows, chunk, st, d_out, nullptr, [&](ScanParams<P>* sp) {
+        scan_params_kernel<P><<<(nrows + 31) / 32, 32, 0, st>>>(kind, q, d, flags, prior, dt_max, d_theta, sp, nrows);
+    });
+}
+
+// One explicit model: the time-parallel form of KalmanFilterp::Filter() with its per-point outputs.
+// d_mean / d_var: [ny] device arrays or nullptr; d_state: [ny][P + P(P+1)/2] or nullptr; d_loglik: one double.
+template <int P>
+static int scan_explicit_p(carma_series* s, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
+                           double* d_loglik, cudaStream_t st) {
+    ScanEmit<P> em{d_mean, d_var, d_state};
+    const double dt_max = s->dt_max;
+    return scan_core<P>(s, 1, 0, st, d_loglik, &em, [&](ScanParams<P>* sp) {
+        scan_params_explicit_kernel<P><<<1, 32, 0, st>>>(ex, dt_max, sp);
+    });
+}
+
+int scan_explicit(carma_series* s, int p, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
+                  double* d_loglik, cudaStream_t st) {
+    switch (p) {
+        case 1: return scan_explicit_p<1>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 2: return scan_explicit_p<2>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 3: return scan_explicit_p<3>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 4: return scan_explicit_p<4>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 5: return scan_explicit_p<5>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 6: return scan_explicit_p<6>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 7: return scan_explicit_p<7>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        default: return CARMA_ERR_ARG;
+    }
 }
 
 }  // namespace carma

@@ -36,7 +36,7 @@ struct carma_series {
     double dt_max = 1.0;  // longest sampling gap
     std::vector<double> t, y, yerr;
     carma::SeriesStats st{};
-    carma::DevBuf scratch_in, scratch_out, scratch_misc;
+    carma::DevBuf scratch_in, scratch_out, scratch_misc, scratch_state;
     // two pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
     carma::DevBuf slot_in[2], slot_out[2];
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
@@ -81,6 +81,12 @@ struct carma_multi_series {
 };
 
 namespace carma {
+// Arrange p roots closed under conjugation into the slots of the real-half recursion (ExplicitModel).
+// Returns false when the set is not conjugate-symmetric (then only the general complex kernels apply).
+bool arrange_roots(const double* omega_reim, const double* ma, int p, double sigsqr, double scale, double mu, ExplicitModel* out);
+// scan.cu: time-parallel Filter() of one explicit model with per-point outputs (device pointers, may be null)
+int scan_explicit(carma_series* s, int p, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
+                  double* d_loglik, cudaStream_t st);
 SeriesStats compute_stats(const double* t, const double* y, size_t n);
 void prior_from_stats(const SeriesStats& st, int population_var, carma_prior_t* out);
 }  // namespace carma

@@ -268,20 +268,36 @@ __host__ __device__ __forceinline__ bool vandermonde_solve_last_smem(const cxd* 
 // lu_scratch (optional, SMEM_LU): this thread's slot of a shared-memory scratch of 2 P^2 doubles per thread,
 // laid out [element][thread] with `lu_stride` threads (see vandermonde_solve_last_smem).
 // dt_max: longest sampling gap of the series the parameters will be used on (rate clamp, see RATE_CAP_STEPS).
+// A model given by its state-space parameters instead of theta (the KalmanFilterp class API: sigsqr, omega, ma --
+// kfilter.hpp:303-334).  The roots must be closed under conjugation and arranged in slots by the host (series.h:
+// arrange_roots): slot s holds a conjugate pair (first root Im <= 0, bit s of cmask set) or two real roots, an odd
+// order ends with one real root.
+struct ExplicitModel {
+    double sigsqr, scale, mu;
+    double w_re[MAX_P], w_im[MAX_P];
+    double ma[MAX_P];
+    unsigned cmask;
+};
+
 // FAST: the reciprocal-multiply divisions above (hot path); !FAST: IEEE divisions (reached only when the fast
 // evaluation produced a non-finite constant, i.e. some denominator left the normal range).
-template <int P, bool WITH_V, bool SMEM_LU, bool FAST>
+// EXPLICIT: roots, MA coefficients, sigma^2, scale and mu come from `ex` (no bounds, no prior); th is not read.
+template <int P, bool WITH_V, bool SMEM_LU, bool FAST, bool EXPLICIT = false>
 __host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsigned flags, const carma_prior_t& pr,
                                                           const double* th, double dt_max, RealParams<P>& out, double* Vr,
-                                                          double* lu_scratch, int lu_stride) {
+                                                          double* lu_scratch, int lu_stride, const ExplicitModel* ex = nullptr) {
     constexpr double PI = 3.14159265358979323846;
-    const double ysigma = th[0], scale = th[1];
+    const double ysigma = EXPLICIT ? 0.0 : th[0], scale = EXPLICIT ? ex->scale : th[1];
     out.scale = scale;
-    out.mu = th[2];
+    out.mu = EXPLICIT ? ex->mu : th[2];
 
     cxd w[P];
     unsigned cmask = 0;
-    if (kind == CARMA_KIND_CAR1) {
+    if (EXPLICIT) {
+#pragma unroll
+        for (int i = 0; i < P; i++) w[i] = cx(ex->w_re[i], ex->w_im[i]);
+        cmask = ex->cmask;
+    } else if (kind == CARMA_KIND_CAR1) {
         // carpack.hpp:265: omega = exp(theta3); the state-space root is -omega
         w[0] = cx(-exp(th[3]), 0.0);
     } else {
@@ -290,7 +306,9 @@ __host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsig
     out.cmask = cmask;
 
     // ---- prior bounds
-    if (kind == CARMA_KIND_CAR1) {
+    if (EXPLICIT) {
+        // none: an explicit model is taken as given
+    } else if (kind == CARMA_KIND_CAR1) {
         double omega = -w[0].re;
         if ((omega > pr.max_freq) || (omega < pr.min_freq) || (ysigma > pr.max_stdev) || (ysigma < 0) ||
             (scale < 0.5) || (scale > 2.0))
@@ -361,7 +379,10 @@ __host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsig
     double ma[P];
 #pragma unroll
     for (int i = 0; i < P; i++) ma[i] = (i == 0) ? 1.0 : 0.0;
-    if (kind == CARMA_KIND_CARMA && q > 0) {
+    if (EXPLICIT) {
+#pragma unroll
+        for (int i = 0; i < P; i++) ma[i] = ex->ma[i];
+    } else if (kind == CARMA_KIND_CARMA && q > 0) {
         cxd r[P];
 #pragma unroll
         for (int i = 0; i < P; i++) r[i] = cx(0, 0);
@@ -424,7 +445,9 @@ __host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsig
         var_acc = var_acc + cdiv_<FAST>(s1 * s2, denom);
     }
     double sigsqr;
-    if (kind == CARMA_KIND_CAR1)
+    if (EXPLICIT)
+        sigsqr = ex->sigsqr;
+    else if (kind == CARMA_KIND_CAR1)
         sigsqr = 2.0 * ysigma * ysigma * (-w[0].re);  // carpack.hpp:272-274
     else
         sigsqr = div_<FAST>(ysigma * ysigma, var_acc.re);  // carpack.hpp:316-319, 391-395
@@ -532,7 +555,7 @@ __host__ __device__ __noinline__ int transform_theta_impl(int kind, int q, unsig
 
     // ---- log prior (carpack.hpp:118-126, 444-456)
     double lp = 0.0;
-    if (!(flags & CARMA_LOGLIK_ONLY)) {
+    if (!EXPLICIT && !(flags & CARMA_LOGLIK_ONLY)) {
         lp = -0.5 * pr.measerr_dof / scale - (1.0 + pr.measerr_dof / 2.0) * log(scale);
         if (kind == CARMA_KIND_ZCARMA) {
             double x = th[3 + P];
@@ -555,6 +578,22 @@ __host__ __device__ __forceinline__ int transform_theta(int kind, int q, unsigne
 #pragma unroll
         for (int i = 0; i < P; i++) chk += out.h[i];
         if (!isfinite(chk)) st = transform_theta_impl<P, WITH_V, SMEM_LU, false>(kind, q, flags, pr, th, dt_max, out, Vr, lu_scratch, lu_stride);
+    }
+    return st;
+}
+
+// The constants of the recursion for an explicit model (fast divisions first, IEEE divisions if anything is not finite).
+template <int P, bool WITH_V = false>
+__host__ __device__ __forceinline__ int explicit_constants(const ExplicitModel& ex, double dt_max, RealParams<P>& out,
+                                                           double* Vr = nullptr) {
+    const carma_prior_t pr{};
+    int st = transform_theta_impl<P, WITH_V, false, true, true>(CARMA_KIND_CARMA, 0, 0u, pr, nullptr, dt_max, out, Vr, nullptr, 0, &ex);
+    if (st == TT_OK) {
+        double chk = out.v0;
+#pragma unroll
+        for (int i = 0; i < P; i++) chk += out.h[i];
+        if (!isfinite(chk))
+            st = transform_theta_impl<P, WITH_V, false, false, true>(CARMA_KIND_CARMA, 0, 0u, pr, nullptr, dt_max, out, Vr, nullptr, 0, &ex);
     }
     return st;
 }

@@ -273,3 +273,40 @@ def test_native_optimizer_matches_numpy_twin(cm):
     # argument checking
     with pytest.raises(cm.CarmaError):
         model.series.mle_batch(cm.KIND_CARMA, 3, 1, np.zeros((2, 7)), -np.ones(7), np.ones(7), slot=5)
+
+
+def test_fast_filter_and_predict_equal_the_general_complex_kernels(cm):
+    """KalmanFilterp::Filter / Predict for conjugate-symmetric roots run in the real-half recursion (time-parallel
+    forward filter + per-query coefficient pass resuming from stored states); the general complex kernels
+    (CARMA_PREDICT_GENERAL=1) are the same algorithm written as in kfilter.cpp:138-337.  Both must agree to rounding,
+    for interpolation, forecasts, backcasts, query times that coincide with data times, and real-pair roots."""
+    import os
+    import time as _time
+    from carma_pack_b200 import synth, Series
+    rng = np.random.default_rng(12)
+    for ny, p, q in ((400, 5, 3), (150, 4, 1), (90, 3, 0), (60, 2, 1), (40, 1, 0)):
+        t, y, e = synth.readme_series(ny, 40 + ny)
+        s = Series(t, y, e)
+        if p == 1:
+            roots, ma, sigsqr = np.array([-0.05 + 0j]), np.array([1.0]), 0.3
+        else:
+            th = synth.prior_draws(1, p, q, t, y, rng)[0]
+            if p >= 4:
+                th[3], th[4] = np.log(0.02), np.log(0.9)          # first factor: two real roots
+            cs = cm.CarmaSample(t, y, e, trace=th[None, :], logpost=np.zeros(1), p=p, q=q)
+            sigsqr, roots, ma, mu, scale = cs._params_at(0)
+        tq = np.concatenate([np.linspace(t[0] - 0.1 * (t[-1] - t[0]), t[-1] + 0.2 * (t[-1] - t[0]), 257), t[::7], [t[0], t[-1]]])
+        out = {}
+        for mode in ("0", "1"):
+            os.environ["CARMA_PREDICT_GENERAL"] = mode
+            t0 = _time.perf_counter()
+            out[mode] = (s.filter(sigsqr, roots, ma, measerr_scale=1.1, mu=0.3), s.predict(sigsqr, roots, ma, tq, measerr_scale=1.1, mu=0.3),
+                         _time.perf_counter() - t0)
+        os.environ.pop("CARMA_PREDICT_GENERAL")
+        (m0, v0), (qm0, qv0), _ = out["0"]
+        (m1, v1), (qm1, qv1), _ = out["1"]
+        np.testing.assert_allclose(m0, m1, rtol=1e-9, atol=1e-9 * np.abs(y).max())
+        np.testing.assert_allclose(v0, v1, rtol=1e-9)
+        np.testing.assert_allclose(qm0, qm1, rtol=1e-7, atol=1e-8 * np.abs(y).max())
+        np.testing.assert_allclose(qv0, qv1, rtol=1e-7)
+        s.close()
