@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "carma_filter", "carma_predict",
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
     "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
-    "carma_starting_value", "carma_comm_unique_id", "carma_comm_init_rank", "carma_comm_destroy",
+    "carma_simulate", "carma_starting_value", "carma_comm_unique_id", "carma_comm_init_rank", "carma_comm_destroy",
     "carma_gather_summaries", "carma_gather_summaries_dev",
 ]
 
@@ -127,6 +127,8 @@ def _load():
     L.carma_fp64_peak_tflops.argtypes = [ctypes.c_int, _dp]
     L.carma_philox_dev.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
     L.carma_fastmath_dev.argtypes = [_dp, _dp, _sz, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.carma_simulate.argtypes = [_vp, ctypes.c_double, _dp, _dp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _dp, _sz,
+                                 ctypes.c_uint64, _sz, _dp]
     L.carma_starting_value.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Prior), ctypes.c_uint64,
                                        ctypes.c_uint32, ctypes.c_int, _dp, _dp]
     L.carma_comm_unique_id.argtypes = [ctypes.c_char_p]
@@ -268,6 +270,20 @@ class Series:
         check(lib.carma_predict(self.handle, sigsqr, _ptr(buf), _ptr(m), p, measerr_scale, mu, _ptr(q), q.size,
                                 _ptr(qm), _ptr(qv)), "carma_predict")
         return qm, qv
+
+    def simulate(self, sigsqr, omega, ma, tsim, measerr_scale=1.0, mu=0.0, seed=1, npaths=1):
+        """Conditional simulation of the process at `tsim` given the data (carma_simulate): (npaths, nsim) array."""
+        om = np.asarray(omega, dtype=complex).ravel()
+        p = om.size
+        buf = np.empty(2 * p)
+        buf[0::2], buf[1::2] = om.real, om.imag
+        m = np.zeros(p)
+        m[:len(ma)] = ma
+        q = _c(np.atleast_1d(tsim))
+        out = np.empty((int(npaths), q.size))
+        check(lib.carma_simulate(self.handle, sigsqr, _ptr(buf), _ptr(m), p, measerr_scale, mu, _ptr(q), q.size,
+                                 int(seed), int(npaths), _ptr(out)), "carma_simulate")
+        return out
 
     def pt_run(self, kind, p, q, nsamples, burnin, thin=1, ntemps=10, n_ensembles=1, seed=1, ensemble_offset=0,
                init=None, prior=None, order_mode=0, record_trace=False, tmax=100.0, dof=8, target_rate=0.25,

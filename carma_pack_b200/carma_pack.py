@@ -590,21 +590,16 @@ class CarmaSample(MCMCSample):
         mean, var = self._series.filter(sigsqr, roots, ma, measerr_scale=scale, mu=mu)
         return mean + mu, var
 
-    def simulate(self, time, bestfit="map", seed=None):
+    def simulate(self, time, bestfit="map", seed=None, npaths=1):
         """Conditional simulation of the light curve at `time` given the data (carma_pack.py:830-854 ->
-        KalmanFilterp::Simulate): sequential draw-and-insert, each draw through the GPU Predict."""
-        from . import _carmcmc as m
+        KalmanFilterp::Simulate): one device call for all times and all `npaths` paths (extension: the reference
+        draws one path).  Returns an array of len(time), or (npaths, len(time)) for npaths > 1."""
         idx = self.best_index() if bestfit == "map" else int(bestfit)
         sigsqr, roots, ma, mu, scale = self._params_at(idx)
-        if seed is not None:
-            m.set_seed(int(seed))
-        kf = m.KalmanFilterp(m.vecD(self.time), m.vecD(self.y - mu), m.vecD(np.sqrt(scale) * self.ysig), sigsqr,
-                             m.vecC([complex(r) for r in roots]), m.vecD(ma))
-        order = np.argsort(np.atleast_1d(time))
-        ysim = np.array(kf.Simulate(m.vecD(np.atleast_1d(time)[order])))
-        out = np.empty_like(ysim)
-        out[order] = ysim
-        return out + mu
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0] >> 1)
+        out = self._series.simulate(sigsqr, roots, ma, np.atleast_1d(time), measerr_scale=scale, mu=mu, seed=seed, npaths=npaths)
+        return out[0] if npaths == 1 else out
 
     def psd_credible_band(self, percentile=68.0, nsamples=None, freq=None, seed=0):
         """Numeric part of plot_power_spectrum (carma_pack.py:548-612): pointwise credibility band of the

@@ -101,28 +101,15 @@ std::pair<double, double> KalmanFilter<O>::Predict(double time) {
 
 template <class O>
 vecD KalmanFilter<O>::Simulate(vecD time) {
-    // kfilter.hpp:135-184: for each (sorted) time draw y ~ N(Predict(t)), then insert (t, y, yerr=0)
-    // into the series so that later draws are conditioned on it.
-    std::shared_ptr<DeviceSeries> saved = series_;
-    vecD t0 = series_->time(), y0 = series_->y(), e0 = series_->yerr();
-    std::sort(time.begin(), time.end());
+    // kfilter.hpp:135-184 draws the points one by one, inserting each into the series before the next Predict; the
+    // device draws the whole conditional path at once (carma_simulate: same joint law, O(ny + nsim) work)
+    double s2; vecC om; vecD ma;
+    params(s2, om, ma);
+    std::vector<double> o = flatten(om);
     vecD ysim(time.size());
-    std::mt19937_64 gen(next_run_seed());
-    std::normal_distribution<double> normal(0.0, 1.0);
-    for (size_t i = 0; i < time.size(); i++) {
-        std::pair<double, double> pr = Predict(time[i]);
-        ysim[i] = pr.first + std::sqrt(pr.second) * normal(gen);
-        size_t ins = 0;
-        while (ins < t0.size() && t0[ins] < time[i]) ins++;
-        if (ins < t0.size() && t0[ins] == time[i]) continue;  // coincides with a measured time: keep the measurement
-        t0.insert(t0.begin() + ins, time[i]);
-        y0.insert(y0.begin() + ins, ysim[i]);
-        e0.insert(e0.begin() + ins, 0.0);
-        series_ = std::make_shared<DeviceSeries>(t0, y0, e0);
-    }
-    series_ = saved;
-    mean.assign(series_->size(), 0.0);
-    var.assign(series_->size(), 0.0);
+    if (time.empty()) return ysim;
+    check(carma_simulate(series_->handle(), s2, o.data(), ma.data(), (int)om.size(), 1.0, 0.0, time.data(), time.size(),
+                         next_run_seed(), 1, ysim.data()), "carma_simulate");
     return ysim;
 }
 

@@ -312,14 +312,14 @@ __global__ void predict_kernel(SeriesView sv, FilterArgs a, const double* __rest
 template <int P>
 __global__ void __launch_bounds__(64)
 predict_real_kernel(SeriesView sv, ExplicitModel ex, const double* __restrict__ state, const double* __restrict__ tq, size_t nq,
-                    double* __restrict__ qmean, double* __restrict__ qvar) {
+                    double* __restrict__ qmean, double* __restrict__ qvar /* may be null */) {
     constexpr int NS = P / 2, NT = P * (P + 1) / 2, SD = P + NT;
     MathTab tb;
     tb.load();
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nq) return;
     RealParams<P> prm;
-    if (explicit_constants<P>(ex, sv.dt_max, prm) != TT_OK) { qmean[k] = NAN; qvar[k] = NAN; return; }
+    if (explicit_constants<P>(ex, sv.dt_max, prm) != TT_OK) { qmean[k] = NAN; if (qvar) qvar[k] = NAN; return; }
     const double time = tq[k];
     const int ny = sv.ny;
     int lo = 0, hi = ny;  // ip = number of data times strictly before `time` (kfilter.cpp:223-229)
@@ -348,7 +348,7 @@ predict_real_kernel(SeriesView sv, ExplicitModel ex, const double* __restrict__ 
         pmean = kf.mean;
         pvar = kf.var;
     }
-    if (ip == ny) { qmean[k] = pmean; qvar[k] = pvar; return; }   // forecast: nothing behind the query
+    if (ip == ny) { qmean[k] = pmean; if (qvar) qvar[k] = pvar; return; }   // forecast: nothing behind the query
     // InitializeCoefs (kfilter.cpp:290-312): y* enters as a noiseless pseudo-observation with the predictive law
     double prec = 1.0 / pvar, pm = pmean * prec;
     double zs[P];
@@ -379,7 +379,62 @@ predict_real_kernel(SeriesView sv, ExplicitModel ex, const double* __restrict__ 
     }
     pvar = 1.0 / prec;
     qmean[k] = pm * pvar;
-    qvar[k] = pvar;
+    if (qvar) qvar[k] = pvar;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditional simulation (KalmanFilter<>::Simulate, kfilter.hpp:135-184) by Matheron's rule: a draw of the process at
+// the requested times GIVEN the data is   f_prior(t*) + E[f(t*) | data'],   data' = (y - mu) - f_prior(T) - eps,
+// with f_prior an unconditional draw of the process on the merged grid (data times T and requested times t*) and eps
+// fresh measurement noise.  O(ny + nsim) work per path instead of the reference's insert-and-re-predict loop
+// (O(nsim (ny + nsim))), and every path of a call is independent: one thread draws one prior path (innovations form
+// of the noise-free filter, as simulate_kernel), the conditional mean comes from the fast Predict above.
+// ---------------------------------------------------------------------------------------------
+enum { STREAM_CONDSIM = 5 };
+
+template <int P>
+__global__ void __launch_bounds__(64)
+sim_prior_kernel(ExplicitModel ex, double dt_max, int nm, const double* __restrict__ dtm /* nm: gap to next merged point */,
+                 const int* __restrict__ idx /* nm: >= 0 data index, < 0: -(sim index) - 1 */, const double* __restrict__ y,
+                 const double* __restrict__ yerr, int ny, int nsim, unsigned long long seed, int npaths,
+                 double* __restrict__ yres /* [npaths][nyp] residual data */, int nyp, double* __restrict__ fsim /* [npaths][nsim] */) {
+    MathTab tb;
+    tb.load();
+    const int path = blockIdx.x * blockDim.x + threadIdx.x;
+    if (path >= npaths) return;
+    RealParams<P> prm;
+    if (explicit_constants<P>(ex, dt_max, prm) != TT_OK) {
+        for (int i = 0; i < nsim; i++) fsim[(size_t)path * nsim + i] = NAN;
+        return;
+    }
+    const double mu = prm.mu, sscale = sqrt(prm.scale);
+    prm.scale = 0.0;   // the process itself carries no measurement noise
+    KalmanReal<P> kf;
+    kf.reset(prm, 0.0);
+    for (int k = 0; k < nm; k++) {
+        double u0, u1;
+        uniforms2(seed, (uint32_t)path, STREAM_CONDSIM, (uint32_t)k, 0u, &u0, &u1);
+        const double rr = sqrt(-2.0 * log(u0));
+        double sn, cs;
+        sincos(6.283185307179586476925286766559 * u1, &sn, &cs);
+        const double var = fmax(kf.var, 0.0);
+        const double innov = sqrt(var) * rr * cs;
+        const double f = kf.mean + innov;
+        const int id = idx[k];
+        if (id >= 0) yres[(size_t)path * nyp + id] = (y[id] - mu) - f - sscale * yerr[id] * rr * sn;   // second normal: eps
+        else fsim[(size_t)path * nsim + (-id - 1)] = f;
+        if (k + 1 < nm) {
+            // a point that coincides with the previous one (var = 0) carries no new information
+            const double inv = kf.var > 1e-300 ? 1.0 / kf.var : 0.0;
+            kf.measurement_update(innov, inv);
+            kf.template predict_observe<false>(prm, tb, dtm[k], 0.0);
+        }
+    }
+}
+
+__global__ void add_prior_kernel(const double* __restrict__ fsim, double mu, size_t n, double* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = out[i] + fsim[i] + mu;
 }
 
 bool arrange_roots(const double* om, const double* ma, int p, double sigsqr, double scale, double mu, ExplicitModel* out) {
@@ -880,6 +935,103 @@ int carma_predict(carma_series_t s, double sigsqr, const double* omega_reim, con
     if (!cuda_ok(cudaMemcpy(qmean, d_m, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qmean")) return CARMA_ERR_CUDA;
     if (!cuda_ok(cudaMemcpy(qvar, d_v, nq * sizeof(double), cudaMemcpyDeviceToHost), "D2H qvar")) return CARMA_ERR_CUDA;
     return CARMA_OK;
+}
+
+// ---- conditional simulation -------------------------------------------------------------------
+int carma_simulate(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p, double measerr_scale,
+                   double mu, const double* tsim, size_t nsim, uint64_t seed, size_t npaths, double* ysim) {
+    if (!s || !omega_reim || !ma || !tsim || !ysim) { set_error("carma_simulate: null argument"); return CARMA_ERR_ARG; }
+    if (nsim == 0 || npaths == 0) return CARMA_OK;
+    ExplicitModel ex;
+    if (!arrange_roots(omega_reim, ma, p, sigsqr, measerr_scale, mu, &ex)) {
+        set_error("carma_simulate: the AR roots must be distinct and closed under complex conjugation (1 <= p <= 7)");
+        return CARMA_ERR_ARG;
+    }
+    for (size_t i = 0; i < nsim; i++)
+        if (!std::isfinite(tsim[i])) { set_error("carma_simulate: non-finite time"); return CARMA_ERR_ARG; }
+    if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    const size_t ny = s->ny, nm = ny + nsim;
+    // merged grid: data points and requested points in time order (a requested time equal to a data time follows it)
+    std::vector<size_t> order(nsim);
+    for (size_t i = 0; i < nsim; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tsim[a] < tsim[b]; });
+    std::vector<double> tm(nm), dtm(nm, 0.0);
+    std::vector<int> idx(nm);
+    size_t a = 0, b = 0;
+    for (size_t k = 0; k < nm; k++) {
+        if (b >= nsim || (a < ny && s->t[a] <= tsim[order[b]])) { tm[k] = s->t[a]; idx[k] = (int)a; a++; }
+        else { tm[k] = tsim[order[b]]; idx[k] = -(int)order[b] - 1; b++; }
+    }
+    double dt_max = s->dt_max;
+    for (size_t k = 0; k + 1 < nm; k++) { dtm[k] = tm[k + 1] - tm[k]; dt_max = std::max(dt_max, dtm[k]); }
+    const size_t state_doubles = ny * (size_t)(p + p * (p + 1) / 2);
+    char* base = nullptr;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_dtm = al(nm * 8), b_idx = al(nm * 4), b_yerr = al(ny * 8), b_yres = al(npaths * ny * 8), b_fsim = al(npaths * nsim * 8),
+                 b_tq = al(nsim * 8), b_state = al((state_doubles + 2) * 8), b_out = al(npaths * nsim * 8);
+    if (!cuda_ok(cudaMalloc((void**)&base, b_dtm + b_idx + b_yerr + b_yres + b_fsim + b_tq + b_state + b_out), "cudaMalloc(simulate)"))
+        return CARMA_ERR_CUDA;
+    double* d_dtm = (double*)base;
+    int* d_idx = (int*)(base + b_dtm);
+    double* d_yerr = (double*)(base + b_dtm + b_idx);
+    double* d_yres = (double*)((char*)d_yerr + b_yerr);
+    double* d_fsim = (double*)((char*)d_yres + b_yres);
+    double* d_tq = (double*)((char*)d_fsim + b_fsim);
+    double* d_state = (double*)((char*)d_tq + b_tq);
+    double* d_ll = d_state + state_doubles;
+    double* d_out = (double*)((char*)d_state + b_state);
+    SeriesView sv = s->view();
+    bool ok = cuda_ok(cudaMemcpy(d_dtm, dtm.data(), nm * 8, cudaMemcpyHostToDevice), "H2D dtm") &&
+              cuda_ok(cudaMemcpy(d_idx, idx.data(), nm * 4, cudaMemcpyHostToDevice), "H2D idx") &&
+              cuda_ok(cudaMemcpy(d_yerr, s->yerr.data(), ny * 8, cudaMemcpyHostToDevice), "H2D yerr") &&
+              cuda_ok(cudaMemcpy(d_tq, tsim, nsim * 8, cudaMemcpyHostToDevice), "H2D tsim");
+    int rc = CARMA_OK;
+    if (ok) {
+        const unsigned g = (unsigned)((npaths + 63) / 64);
+#define LAUNCH_SP(PP) sim_prior_kernel<PP><<<g, 64>>>(ex, dt_max, (int)nm, d_dtm, d_idx, sv.y, d_yerr, (int)ny, (int)nsim, seed, (int)npaths, d_yres, (int)ny, d_fsim)
+        switch (p) {
+            case 1: LAUNCH_SP(1); break;
+            case 2: LAUNCH_SP(2); break;
+            case 3: LAUNCH_SP(3); break;
+            case 4: LAUNCH_SP(4); break;
+            case 5: LAUNCH_SP(5); break;
+            case 6: LAUNCH_SP(6); break;
+            default: LAUNCH_SP(7); break;
+        }
+#undef LAUNCH_SP
+        ok = cuda_ok(cudaGetLastError(), "sim_prior_kernel launch");
+    }
+    ExplicitModel ex0 = ex;
+    ex0.mu = 0.0;   // the residual data are already centred
+    for (size_t path = 0; ok && path < npaths; path++) {
+        const double* d_y = d_yres + path * ny;
+        rc = scan_explicit(s, p, ex0, nullptr, nullptr, d_state, d_ll, 0, d_y);
+        if (rc) { ok = false; break; }
+        SeriesView svp = sv;
+        svp.y = d_y;
+        const unsigned g64 = (unsigned)((nsim + 63) / 64);
+#define LAUNCH_PR(PP) predict_real_kernel<PP><<<g64, 64>>>(svp, ex0, d_state, d_tq, nsim, d_out + path * nsim, nullptr)
+        switch (p) {
+            case 1: LAUNCH_PR(1); break;
+            case 2: LAUNCH_PR(2); break;
+            case 3: LAUNCH_PR(3); break;
+            case 4: LAUNCH_PR(4); break;
+            case 5: LAUNCH_PR(5); break;
+            case 6: LAUNCH_PR(6); break;
+            default: LAUNCH_PR(7); break;
+        }
+#undef LAUNCH_PR
+        ok = cuda_ok(cudaGetLastError(), "predict_real_kernel launch");
+    }
+    if (ok) {
+        const size_t n = npaths * nsim;
+        add_prior_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_fsim, mu, n, d_out);
+        ok = cuda_ok(cudaGetLastError(), "add_prior_kernel launch") &&
+             cuda_ok(cudaMemcpy(ysim, d_out, n * 8, cudaMemcpyDeviceToHost), "D2H ysim");
+    }
+    cudaFree(base);
+    if (rc) return rc;
+    return ok ? CARMA_OK : CARMA_ERR_CUDA;
 }
 
 // ---- utilities --------------------------------------------------------------------------------

@@ -579,8 +579,9 @@ scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict_
 // pass 3 also writes the per-point predictive mean / variance / state.
 template <int P, class FillParams>
 static int scan_core(carma_series* s, int nrows, int chunk, cudaStream_t st, double* d_out, const ScanEmit<P>* em,
-                     FillParams fill_params) {
+                     FillParams fill_params, const double* d_y_override = nullptr) {
     SeriesView sv = s->view();
+    if (d_y_override) sv.y = d_y_override;   // same times and errors, other values (conditional simulation)
     if (chunk <= 0) chunk = 128;
     chunk = std::max(chunk, 2);
     // two scan levels of 256 cover 65,536 aggregates: longer series get longer chunks
@@ -636,24 +637,24 @@ static int scan_rows(carma_series* s, int kind, int q, unsigned flags, const car
 // d_mean / d_var: [ny] device arrays or nullptr; d_state: [ny][P + P(P+1)/2] or nullptr; d_loglik: one double.
 template <int P>
 static int scan_explicit_p(carma_series* s, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
-                           double* d_loglik, cudaStream_t st) {
+                           double* d_loglik, cudaStream_t st, const double* d_y_override) {
     ScanEmit<P> em{d_mean, d_var, d_state};
     const double dt_max = s->dt_max;
     return scan_core<P>(s, 1, 0, st, d_loglik, &em, [&](ScanParams<P>* sp) {
         scan_params_explicit_kernel<P><<<1, 32, 0, st>>>(ex, dt_max, sp);
-    });
+    }, d_y_override);
 }
 
 int scan_explicit(carma_series* s, int p, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
-                  double* d_loglik, cudaStream_t st) {
+                  double* d_loglik, cudaStream_t st, const double* d_y_override) {
     switch (p) {
-        case 1: return scan_explicit_p<1>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 2: return scan_explicit_p<2>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 3: return scan_explicit_p<3>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 4: return scan_explicit_p<4>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 5: return scan_explicit_p<5>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 6: return scan_explicit_p<6>(s, ex, d_mean, d_var, d_state, d_loglik, st);
-        case 7: return scan_explicit_p<7>(s, ex, d_mean, d_var, d_state, d_loglik, st);
+        case 1: return scan_explicit_p<1>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 2: return scan_explicit_p<2>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 3: return scan_explicit_p<3>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 4: return scan_explicit_p<4>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 5: return scan_explicit_p<5>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 6: return scan_explicit_p<6>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
+        case 7: return scan_explicit_p<7>(s, ex, d_mean, d_var, d_state, d_loglik, st, d_y_override);
         default: return CARMA_ERR_ARG;
     }
 }

@@ -86,7 +86,7 @@ namespace carma {
 bool arrange_roots(const double* omega_reim, const double* ma, int p, double sigsqr, double scale, double mu, ExplicitModel* out);
 // scan.cu: time-parallel Filter() of one explicit model with per-point outputs (device pointers, may be null)
 int scan_explicit(carma_series* s, int p, const ExplicitModel& ex, double* d_mean, double* d_var, double* d_state,
-                  double* d_loglik, cudaStream_t st);
+                  double* d_loglik, cudaStream_t st, const double* d_y_override = nullptr);
 SeriesStats compute_stats(const double* t, const double* y, size_t n);
 void prior_from_stats(const SeriesStats& st, int population_var, carma_prior_t* out);
 }  // namespace carma

@@ -195,6 +195,17 @@ int carma_filter(carma_series_t s, double sigsqr, const double* omega_reim, cons
 int carma_predict(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
                   double measerr_scale, double mu, const double* tq, size_t nq, double* qmean, double* qvar);
 
+/* Replaces KalmanFilter<>::Simulate (src/include/kfilter.hpp:135-184): draws of the process at the times tsim (any
+ * order; may coincide with data times) GIVEN the data, for `npaths` independent paths in one call:
+ * ysim[path * nsim + i].  The reference draws one point at a time, inserts it into the series and re-predicts
+ * (O(nsim (ny + nsim)) filter steps); here every path is an unconditional draw on the merged time grid plus the
+ * conditional mean of the residual data (Matheron's rule): same joint law, O(ny + nsim) work per path, no per-point
+ * allocation or host round trip.  Random numbers: Philox4x32-10 addressed by (seed, path, merged index).  The AR roots
+ * must be distinct and closed under complex conjugation. */
+int carma_simulate(carma_series_t s, double sigsqr, const double* omega_reim, const double* ma, int p,
+                   double measerr_scale, double mu, const double* tsim, size_t nsim, uint64_t seed, size_t npaths,
+                   double* ysim);
+
 /* ---- parallel-tempering MCMC, fully on device ---------------------------------------------
  * Replaces RunCarmaSampler / RunCar1Sampler (src/carmcmc.cpp:30-177): temperature ladder,
  * AdaptiveMetro (src/steps.cpp:24-107), CholUpdateR1 (111-131), ExchangeStep

@@ -310,3 +310,53 @@ def test_fast_filter_and_predict_equal_the_general_complex_kernels(cm):
         np.testing.assert_allclose(qm0, qm1, rtol=1e-7, atol=1e-8 * np.abs(y).max())
         np.testing.assert_allclose(qv0, qv1, rtol=1e-7)
         s.close()
+
+
+def test_device_simulate_matches_the_exact_gaussian_process_conditional(cm):
+    """carma_simulate (KalmanFilter<>::Simulate, kfilter.hpp:135-184; reference test carma_unit_tests.cpp:651-780):
+    4,000 conditional paths in ONE call on a 60-point series.  The draws, whitened with the exact conditional mean and
+    covariance of the Gaussian process (dense ny x ny algebra with carma_variance as the kernel), must be white
+    N(0, 1): sample mean and covariance of the whitened draws within Monte-Carlo error, for times inside gaps, on top
+    of data times, before the first and after the last point."""
+    from carma_pack_b200 import synth, Series
+    rng = np.random.default_rng(5)
+    roots = synth.get_ar_roots(np.array([0.05, 0.02]), np.array([0.12]))      # CARMA(3,1): one pair + one real root
+    ma = np.array([1.0, 2.5, 0.0])
+    sigsqr = 1.7 ** 2 / synth.carma_variance(1.0, roots, ma)
+    ny = 60
+    t = np.cumsum(rng.uniform(0.5, 4.0, ny))
+    y0 = synth.carma_process(t, sigsqr, roots, ma, rng=rng)
+    e = rng.uniform(0.1, 0.4, ny)
+    y = 3.0 + y0 + e * rng.standard_normal(ny)
+    mu, scale = 3.0, 1.2
+    tsim = np.concatenate([[t[0] - 7.0, t[0] - 1.0], t[5] + np.array([0.1, 0.3, 1.0]), [t[20]], rng.uniform(t[0], t[-1], 14), [t[-1] + 2.0, t[-1] + 30.0]])
+    s = Series(t, y, e)
+    npaths = 4000
+    sims = s.simulate(sigsqr, roots, ma, tsim, measerr_scale=scale, mu=mu, seed=99, npaths=npaths)
+    assert sims.shape == (npaths, tsim.size) and np.all(np.isfinite(sims))
+    # reproducible, and path j does not depend on how many paths are drawn
+    again = s.simulate(sigsqr, roots, ma, tsim, measerr_scale=scale, mu=mu, seed=99, npaths=7)
+    assert np.array_equal(again, sims[:7])
+    # exact conditional law
+    kern = lambda a, b: np.array([[synth.carma_variance(sigsqr, roots, ma, lag=abs(x - z)) for z in b] for x in a])
+    Kdd = kern(t, t) + np.diag(scale * e ** 2)
+    Ksd = kern(tsim, t)
+    Kss = kern(tsim, tsim)
+    sol = np.linalg.solve(Kdd, (y - mu))
+    cmean = mu + Ksd @ sol
+    ccov = Kss - Ksd @ np.linalg.solve(Kdd, Ksd.T)
+    # the conditional mean is also what Predict returns
+    pm, pv = s.predict(sigsqr, roots, ma, tsim, measerr_scale=scale, mu=mu)
+    np.testing.assert_allclose(pm + mu, cmean, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(pv, np.diag(ccov), rtol=1e-6, atol=1e-10)
+    s.close()
+    # the draw at a data time is NOT the datum (measurement noise): the conditional variance there is > 0
+    w, V = np.linalg.eigh(ccov)
+    keep = w > 1e-9 * w.max()
+    white = (sims - cmean) @ V[:, keep] / np.sqrt(w[keep])
+    n = npaths
+    assert np.all(np.abs(white.mean(axis=0)) < 4.5 / np.sqrt(n)), np.abs(white.mean(axis=0)).max()
+    C_ = np.cov(white.T)
+    assert np.all(np.abs(np.diag(C_) - 1.0) < 5.0 * np.sqrt(2.0 / n)), np.abs(np.diag(C_) - 1.0).max()
+    off = C_ - np.diag(np.diag(C_))
+    assert np.abs(off).max() < 5.0 / np.sqrt(n), np.abs(off).max()
