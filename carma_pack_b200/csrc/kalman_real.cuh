@@ -306,6 +306,48 @@ CARMA_HD void filter_span_impl(KalmanReal<P>& kf, LogLikAcc& acc, const RealPara
     }
 }
 
+// Software-pipelined form for launches with ONE OR TWO warps per SM (a single PT ensemble: the reference's own use,
+// BASELINE config 1), where nothing hides latency: the transition blocks of step i + 1 -- table lookups and ~70 FP64
+// instructions that depend only on dt, not on the filter state -- are computed in the same basic block as the state
+// update of step i, so their latency no longer sits on the recursion's critical path (rcp -> gain -> D update ->
+// predict -> observe).  Same operations, same results, bit for bit.  Costs ~10 registers.  Measured: no gain once the
+// SM holds >= 8 warps (config 3: 4.09 vs 4.11e6 ensemble-iterations/s), so pt_kernel selects it only for small grids.
+// Requires src.get(nadv) to be readable (the staged series is padded: dt[ny-1] = 0).
+template <int P, bool ALLC, class Src, class Tab>
+CARMA_HD void filter_span_pipelined(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
+                                    const Src& src, int len, int nadv) {
+    constexpr int NS = KalmanReal<P>::NS;
+    double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo = 1.0;
+    double y_c = 0.0, dt_c = 0.0, e_c = 0.0;
+    if (len > 0) src.get(0, &dt_c, &y_c, &e_c);
+    if (nadv > 0) KalmanReal<P>::template transition<ALLC>(prm, tb, dt_c, fa, fb, fsb, &fo);
+    for (int i0 = 0; i0 < nadv; i0 += RENORM_EVERY) {
+        const int i1 = (nadv - i0 < RENORM_EVERY) ? nadv : i0 + RENORM_EVERY;
+        for (int i = i0; i < i1; i++) {
+            double na[NS > 0 ? NS : 1], nb[NS > 0 ? NS : 1], nsb[NS > 0 ? NS : 1], no;
+            double y_n, dt_n, e_n;
+            src.get(i + 1, &dt_n, &y_n, &e_n);
+            KalmanReal<P>::template transition<ALLC>(prm, tb, dt_n, na, nb, nsb, &no);
+            const double innov = (y_c - prm.mu) - kf.mean;
+            const double inv = rcp_fast(kf.var);
+            acc.add(kf.var, innov, inv);
+            kf.measurement_update(innov, inv);
+            kf.propagate(prm, fa, fb, fsb, fo, e_c);
+#pragma unroll
+            for (int s = 0; s < NS; s++) { fa[s] = na[s]; fb[s] = nb[s]; fsb[s] = nsb[s]; }
+            fo = no;
+            y_c = y_n; e_c = e_n;
+        }
+        acc.renorm(i1 - i0);
+    }
+    if (nadv < len) {
+        const double innov = (y_c - prm.mu) - kf.mean;
+        const double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+        acc.renorm(1);
+    }
+}
+
 template <int P, bool PF, class Src, class Tab>
 CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
                               const Src& src, int len, int nadv) {
@@ -320,6 +362,19 @@ CARMA_HD void filter_span_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParam
 #endif
     if (all_c) filter_span_impl<P, true, PF>(kf, acc, prm, tb, src, len, nadv);
     else filter_span_impl<P, false, PF>(kf, acc, prm, tb, src, len, nadv);
+}
+
+template <int P, class Src, class Tab>
+CARMA_HD void filter_span_any_pipelined(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
+                                        const Src& src, int len, int nadv) {
+    constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
+#ifdef __CUDA_ARCH__
+    const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
+#else
+    const bool all_c = prm.cmask == ALL;
+#endif
+    if (all_c) filter_span_pipelined<P, true>(kf, acc, prm, tb, src, len, nadv);
+    else filter_span_pipelined<P, false>(kf, acc, prm, tb, src, len, nadv);
 }
 
 // Exact (slow) evaluation of the log-likelihood of one theta: the same recursion with one log() per point.

@@ -56,6 +56,7 @@ struct PTParams {
     double dt_max;       // longest gap of the series (all curves in multi mode): rate clamp of transform_theta
     int ny;
     int series_in_smem;  // 1: sdt/sy/se of the log-density calls point into shared memory
+    int pipelined;       // 1: software-pipelined filter loop (few warps per SM: latency bound)
     // device buffers
     const double* init;  // d values or nullptr
     double* samples;     // [n_ens][nsamples][d]
@@ -153,7 +154,8 @@ __device__ __noinline__ double logdensity_resident(const PTParams& pp, const Mat
         // the staged series: LDS off one 32-bit address register
         const uint32_t a = smem_u32(sdt);
         const SeriesSmem src{a, smem_u32(sy) - a, smem_u32(se) - a};
-        filter_span_any<P, false>(kf, acc, prm, tb, src, pp.ny, pp.ny - 1);
+        if (pp.pipelined) filter_span_any_pipelined<P>(kf, acc, prm, tb, src, pp.ny, pp.ny - 1);
+        else filter_span_any<P, false>(kf, acc, prm, tb, src, pp.ny, pp.ny - 1);
     } else {
         filter_span_any<P, true>(kf, acc, prm, tb, gsrc, pp.ny, pp.ny - 1);
     }
@@ -596,6 +598,11 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
     // series resident in shared memory when it fits (<= 96 KiB keeps at least two blocks per SM)
     mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= PT_SMEM_MAX ? 1 : 0;
     pp.series_in_smem = mm.resident;
+    {
+        // latency-bound regime (at most ~2 blocks per SM): pipelined loop; CARMA_PT_PIPE=0/1 overrides (measurements)
+        const char* e = getenv("CARMA_PT_PIPE");
+        pp.pipelined = e ? (e[0] == '1') : (grid <= 2u * 148u);
+    }
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
     if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;

@@ -24,7 +24,8 @@ static double one(int kind, int q, unsigned flags, const carma_prior_t& pr, cons
     LogLikAcc acc;
     kf.reset(prm, e2_0);
     acc.init();
-    if (force_generic) filter_span_impl<P, false, false>(kf, acc, prm, tb, src, ny, ny - 1);
+    if (force_generic == 2) filter_span_any_pipelined<P>(kf, acc, prm, tb, src, ny, ny - 1);
+    else if (force_generic) filter_span_impl<P, false, false>(kf, acc, prm, tb, src, ny, ny - 1);
     else filter_span_any<P, false>(kf, acc, prm, tb, src, ny, ny - 1);
     if (acc.bad()) return loglik_exact_slow<P>(prm, tb, src, ny, e2_0) + prm.logprior;
     return acc.value() + prm.logprior;

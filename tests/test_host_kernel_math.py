@@ -80,6 +80,9 @@ def test_config2_shape_against_oracle(H):
     # warp-composition independence: the generic loop gives the same bits as the all-conjugate loop
     gen = host_loglik(H, O.KIND_CARMA, 5, 3, t, y, e, th, pr, force_generic=1)
     assert np.array_equal(np.nan_to_num(gen, nan=1.5, neginf=2.5), np.nan_to_num(got, nan=1.5, neginf=2.5))
+    # the software-pipelined loop (single-ensemble PT runs) performs the same operations: same bits
+    pip = host_loglik(H, O.KIND_CARMA, 5, 3, t, y, e, th, pr, force_generic=2)
+    assert np.array_equal(np.nan_to_num(pip, nan=1.5, neginf=2.5), np.nan_to_num(got, nan=1.5, neginf=2.5))
 
 
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7])
