@@ -39,6 +39,7 @@ namespace carma {
 
 constexpr int PT_BLOCK = 64;
 constexpr size_t PT_SMEM_MAX = 96 * 1024;  // series resident in shared memory up to this size
+constexpr size_t PT_SMEM_HELP_MAX = 200 * 1024;  // helper mode: one block per SM, ring + parameters on top
 
 struct PTParams {
     int kind, q, d;
@@ -163,6 +164,173 @@ __device__ __noinline__ double logdensity_resident(const PTParams& pp, const Mat
     return acc.value() + prm.logprior;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised evaluation for SMALL launches (one ensemble = the reference's own use, or the 100 short runs that
+// seed get_mle): with one or two warps per SM nothing hides latency, and a lone warp needs ~1,150 cycles per Kalman
+// step although it only issues ~300 instructions.  More than half of those instructions -- the transition blocks
+// exp(omega dt) of every slot -- depend on (theta, dt) alone, not on the filter state.  In helper mode a block carries,
+// for each of its two chain warps, TWO producer warps (even / odd steps) that compute these factors ahead of the
+// recursion and hand them over through a ring in shared memory; the chain warp runs only the state recursion
+// (reciprocal, gain, covariance update, propagation, observation: ~135 instructions per step).  Hand-over is by
+// monotone step counters in shared memory (volatile, one writer each), checked once per HELP_CHUNK steps.
+// Same operations on the same values: results are bit-identical to the plain kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HELP_RING = 16;    // steps held in the ring, per chain thread
+constexpr int HELP_CHUNK = 4;    // steps per hand-over check
+constexpr int HELP_GROUPS = 2;   // producer warps per chain warp
+
+template <int P>
+struct HelpShared {
+    static constexpr int NS = P / 2;
+    static constexpr int NF = 2 * NS + 1;            // fa[NS], fb[NS], fo
+    double* ring;                                    // [HELP_RING][NF][PT_BLOCK]
+    double* par;                                     // [P][PT_BLOCK]: le[(P+1)/2], ls[P/2]
+    int* pari;                                       // [PT_BLOCK]: cmask | active << 16
+    volatile int* posted;                            // [2]  evaluations published by chain warp w
+    volatile int* skip;                              // [2]  1: no lane of warp w evaluates in this tick
+    volatile int* produced;                          // [HELP_GROUPS][2]  steps (absolute count) produced so far
+    volatile int* consumed;                          // [2]
+    static size_t doubles() { return (size_t)HELP_RING * NF * PT_BLOCK + (size_t)P * PT_BLOCK + PT_BLOCK / 2 + 8; }
+    __device__ void carve(double* base) {
+        ring = base;
+        par = ring + (size_t)HELP_RING * NF * PT_BLOCK;
+        pari = (int*)(par + (size_t)P * PT_BLOCK);
+        int* flags = pari + PT_BLOCK;
+        posted = flags; skip = flags + 2; produced = flags + 4; consumed = flags + 8;
+    }
+};
+
+__device__ __forceinline__ void spin_until(volatile int* flag, int target) {
+    while ((int)(*flag - target) < 0) {
+    }
+    __threadfence_block();
+}
+
+// chain side: every lane of the chain warp calls this together; `want` = this lane evaluates theta `th`
+template <int P>
+__device__ __noinline__ double logdensity_assisted(const PTParams& pp, const MathTab& tb, const HelpShared<P>& hs, bool want,
+                                                   const double* th, const double* sy, const double* se, double e2_0,
+                                                   int eval_idx) {
+    constexpr int NS = P / 2, NF = HelpShared<P>::NF;
+    const int t64 = threadIdx.x, w = t64 >> 5, lane = t64 & 31;
+    RealParams<P> prm;
+    bool act = want;
+    if (act) act = transform_theta<P>(pp.kind, pp.q, 0u, pp.prior, th, pp.dt_max, prm) == TT_OK;
+    if (act) {
+#pragma unroll
+        for (int k = 0; k < (P + 1) / 2; k++) hs.par[(size_t)k * PT_BLOCK + t64] = prm.le[k];
+#pragma unroll
+        for (int k = 0; k < NS; k++) hs.par[(size_t)((P + 1) / 2 + k) * PT_BLOCK + t64] = prm.ls[k];
+    }
+    hs.pari[t64] = act ? (int)(prm.cmask | (1u << 16)) : 0;
+    const bool any = __any_sync(0xffffffffu, act);
+    __threadfence_block();
+    __syncwarp();
+    const int nadv = pp.ny - 1;
+    const int base = eval_idx * nadv;
+    if (lane == 0) { hs.skip[w] = any ? 0 : 1; hs.consumed[w] = base; __threadfence_block(); hs.posted[w] = eval_idx + 1; }
+    if (!any) return -INFINITY;
+    KalmanReal<P> kf;
+    LogLikAcc acc;
+    if (act) kf.reset(prm, e2_0);
+    acc.init();
+    const uint32_t ya = smem_u32(sy), ea = smem_u32(se), ra = smem_u32(hs.ring) + 8u * (uint32_t)t64;
+    int since = 0;
+    for (int i0 = 0; i0 < nadv; i0 += HELP_CHUNK) {
+        const int i1 = min(nadv, i0 + HELP_CHUNK);
+        // the factors of steps i0 .. i1-1: even steps come from group 0, odd ones from group 1
+        const int last = i1 - 1;
+        const int last_even = (last & 1) ? last - 1 : last, last_odd = (last & 1) ? last : last - 1;   // i0 is even
+        spin_until(&hs.produced[0 * 2 + w], base + last_even + 1);
+        if (last_odd >= i0) spin_until(&hs.produced[1 * 2 + w], base + last_odd + 1);
+        if (act) {
+            for (int i = i0; i < i1; i++) {
+                double fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo, y_i, e_i;
+                const uint32_t slot = ra + (uint32_t)(i % HELP_RING) * (uint32_t)(NF * PT_BLOCK * 8);
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fa[k]) : "r"(slot + (uint32_t)(k * PT_BLOCK * 8)));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fb[k]) : "r"(slot + (uint32_t)((NS + k) * PT_BLOCK * 8)));
+                    fsb[k] = ((prm.cmask >> k) & 1u) ? -fb[k] : fb[k];
+                }
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(fo) : "r"(slot + (uint32_t)(2 * NS * PT_BLOCK * 8)));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(y_i) : "r"(ya + 8u * (uint32_t)i));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(e_i) : "r"(ea + 8u * (uint32_t)i));
+                const double innov = (y_i - prm.mu) - kf.mean;
+                const double inv = rcp_fast(kf.var);
+                acc.add(kf.var, innov, inv);
+                kf.measurement_update(innov, inv);
+                kf.propagate(prm, fa, fb, fsb, fo, e_i);
+            }
+            since += i1 - i0;
+            if (since >= RENORM_EVERY - HELP_CHUNK) { acc.renorm(since); since = 0; }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); hs.consumed[w] = base + i1; }
+    }
+    if (!act) return -INFINITY;
+    {
+        double y_l;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(y_l) : "r"(ya + 8u * (uint32_t)nadv));
+        const double innov = (y_l - prm.mu) - kf.mean;
+        const double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+        acc.renorm(since + 1);
+    }
+    if (acc.bad()) return NAN;   // marker: the caller re-evaluates this lane with logdensity_resident (exact slow path inside)
+    return acc.value() + prm.logprior;
+}
+
+// producer side: one warp of group g serving chain warp w, for every tick of the run
+template <int P>
+__device__ __noinline__ void helper_loop(const PTParams& pp, const MathTab& tb, const HelpShared<P>& hs, int g, int w,
+                                         const double* sdt, int nticks, bool sync_each_tick) {
+    constexpr int NS = P / 2, NF = HelpShared<P>::NF;
+    const int lane = threadIdx.x & 31, t64 = w * 32 + lane;
+    const int nadv = pp.ny - 1;
+    const uint32_t da = smem_u32(sdt), ra = smem_u32(hs.ring) + 8u * (uint32_t)t64;
+    for (int e = 0; e < nticks; e++) {
+        spin_until(&hs.posted[w], e + 1);
+        if (!hs.skip[w]) {
+            const int pi = hs.pari[t64];
+            const bool act = (pi >> 16) & 1;
+            RealParams<P> prm;
+            prm.cmask = (unsigned)(pi & 0xffff);
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < (P + 1) / 2; k++) prm.le[k] = hs.par[(size_t)k * PT_BLOCK + t64];
+#pragma unroll
+                for (int k = 0; k < NS; k++) prm.ls[k] = hs.par[(size_t)((P + 1) / 2 + k) * PT_BLOCK + t64];
+            }
+            constexpr unsigned ALL = (NS > 0) ? ((1u << NS) - 1u) : 0u;
+            const bool all_c = __all_sync(0xffffffffu, !act || prm.cmask == ALL);
+            const int base = e * nadv;
+            for (int i = g; i < nadv; i += HELP_GROUPS) {
+                spin_until(&hs.consumed[w], base + i + 1 - HELP_RING);   // slot i % RING was used by step i - RING
+                if (act) {
+                    double dt, fa[NS > 0 ? NS : 1], fb[NS > 0 ? NS : 1], fsb[NS > 0 ? NS : 1], fo;
+                    asm("ld.shared.f64 %0, [%1];" : "=d"(dt) : "r"(da + 8u * (uint32_t)i));
+                    if (all_c) KalmanReal<P>::template transition<true>(prm, tb, dt, fa, fb, fsb, &fo);
+                    else KalmanReal<P>::template transition<false>(prm, tb, dt, fa, fb, fsb, &fo);
+                    const uint32_t slot = ra + (uint32_t)(i % HELP_RING) * (uint32_t)(NF * PT_BLOCK * 8);
+#pragma unroll
+                    for (int k = 0; k < NS; k++) {
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot + (uint32_t)(k * PT_BLOCK * 8)), "d"(fa[k]) : "memory");
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot + (uint32_t)((NS + k) * PT_BLOCK * 8)), "d"(fb[k]) : "memory");
+                    }
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(slot + (uint32_t)(2 * NS * PT_BLOCK * 8)), "d"(fo) : "memory");
+                }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); hs.produced[g * 2 + w] = base + i + 1; }
+            }
+            // steps this group does not own must not leave the counter behind the other group's view of "all done"
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); hs.produced[g * 2 + w] = base + nadv; }
+        }
+        if (sync_each_tick) { __syncthreads(); __syncthreads(); }
+    }
+}
+
 template <int P>
 __device__ double starting_value_attempt(const PTParams& pp, const MathTab& tb, StartRng& g, double* th, const double* sdt,
                                          const double* sy, const double* se, double e2_0) {
@@ -194,17 +362,20 @@ __device__ double starting_value_attempt(const PTParams& pp, const MathTab& tb, 
 
 __device__ __forceinline__ int tri(int k, int j) { return j * (j + 1) / 2 + k; }  // k <= j
 
-template <int P>
 // min blocks/SM = 5 (<= 204 registers): the filter loop then keeps its whole state in registers (ncu r01d:
 // with a 128-register cap the loop spilled 3 loads + 2 stores per step and stalled on them), and
 // 5 x 148 = 740 resident blocks still hold BASELINE config 3 (683 blocks) in a single wave.
-__global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride,
-                                                                        PTMulti mm) {
+// HELP: warp-specialised variant for small launches (see HelpShared): threads [0, 64) are the chains, [64, 192) four
+// producer warps; one block per SM.
+template <int P, bool HELP>
+__global__ void __launch_bounds__(HELP ? PT_BLOCK * (1 + HELP_GROUPS) : PT_BLOCK, HELP ? 1 : (P <= 5 ? 5 : 4))
+pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
 
     PTParams pp = pp_in;
-    const int tid = threadIdx.x;
+    const int tid = HELP ? (threadIdx.x < PT_BLOCK ? threadIdx.x : 0) : threadIdx.x;   // helpers shadow chain thread 0 in the set-up code
+    const bool is_helper = HELP && threadIdx.x >= PT_BLOCK;
     const int T = pp.T, d = pp.d;
     const int epb = PT_BLOCK / T;
     const int e_local = tid / T, i = tid % T;
@@ -228,7 +399,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         // so no bulk copy here); se is the yerr^2 array shifted by one point
         const int curve = blockIdx.x / mm.blocks_per_curve;
         const unsigned long long e_in = (unsigned long long)(blockIdx.x % mm.blocks_per_curve) * epb + e_local;
-        active = (e_local < epb) && (e_in < mm.ens_per_curve);
+        active = !is_helper && (e_local < epb) && (e_in < mm.ens_per_curve);
         ens = (unsigned long long)curve * mm.ens_per_curve + e_in;
         const long long o0 = mm.off[curve];
         const int ny = (int)(mm.off[curve + 1] - o0);
@@ -237,7 +408,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         pp.y_mean = ci.y_mean; pp.y_var_sample = ci.y_var_sample; pp.y_var_pop = ci.y_var_pop;
         pp.median_dt = ci.median_dt; pp.tspan = ci.tspan; pp.ny = ny;
         if (mm.resident) {
-            for (int k = tid; k < ny; k += PT_BLOCK) {
+            for (int k = threadIdx.x; k < ny; k += blockDim.x) {
                 sdt[k] = mm.dt[o0 + k];
                 sy[k] = mm.y[o0 + k];
                 se[k] = mm.e2[o0 + k];
@@ -252,7 +423,7 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         se = se + 1;
     } else {
         ens = (unsigned long long)blockIdx.x * epb + e_local;
-        active = (e_local < epb) && (ens < pp.n_ens);
+        active = !is_helper && (e_local < epb) && (ens < pp.n_ens);
         // ---- stage the light curve once (TMA bulk copy), resident for the whole run; a series that does
         // not fit in shared memory is read from global memory instead (every lane reads the same address:
         // one L1 line per warp, and the filter loop prefetches one step ahead)
@@ -261,12 +432,12 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
             sy = const_cast<double*>(sv.y);
             se = const_cast<double*>(sv.e2n);
         }
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
-        if (tid == 0 && mm.resident) {
+        if (threadIdx.x == 0 && mm.resident) {
             // pieces of at most 64 KiB keep every transaction count far below the mbarrier tx limit
             const uint32_t total = (uint32_t)(3 * (size_t)sv.nyp * 8);
             mbar_expect_tx(&bar, total);
@@ -299,6 +470,21 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         R[(size_t)tri(2, 2) * chol_stride] = sqrt(pp.y_var_pop / (double)pp.ny);
     }
 
+    const int total = pp.total_iters;
+    const int nticks = pp.order_mode == 0 ? total + T - 1 : total;
+
+    HelpShared<P> hs{};
+    if (HELP) {
+        hs.carve(xu + PT_BLOCK);
+        if (threadIdx.x < 10) ((int*)hs.posted)[threadIdx.x] = 0;   // posted[2], skip[2], produced[4], consumed[2]
+        __syncthreads();
+        if (is_helper) {
+            const int hw = (threadIdx.x - PT_BLOCK) >> 5;            // helper warp 0..3: group = hw >> 1, chain warp = hw & 1
+            helper_loop<P>(pp, tb, hs, hw >> 1, hw & 1, sdt, nticks, T > 1);
+            return;
+        }
+    }
+
     // ---- starting values (samplers.cpp:75-93)
     if (active) {
         bool ok = false;
@@ -317,16 +503,13 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
         if (!ok) atomicExch(pp.status, 1);
     }
 
-    const int total = pp.total_iters;
-    const int nticks = pp.order_mode == 0 ? total + T - 1 : total;
-
     for (int tick = 0; tick < nticks; tick++) {
         const int n = pp.order_mode == 0 ? tick - (T - 1 - i) : tick;
         const bool stepping = active && n >= 0 && n < total;
+        double z[MAX_D], sp[MAX_D], nv[MAX_D];
+        double znorm2 = 0.0, lpn = -INFINITY;
         if (stepping) {
             // ---- AdaptiveMetro::DoStep (steps.cpp:60-107)
-            double z[MAX_D], sp[MAX_D], nv[MAX_D];
-            double znorm2 = 0.0;
             for (int j = 0; j < d; j++) {
                 z[j] = tdist_draw(pp.seed, chain, STREAM_PROPOSAL, (uint32_t)n, (uint32_t)j, pp.dof);
                 znorm2 += z[j] * z[j];
@@ -338,7 +521,15 @@ __global__ void __launch_bounds__(PT_BLOCK, (P <= 5 ? 5 : 4)) pt_kernel(SeriesVi
                 nv[j] = th[j] + s;
             }
             for (int j = d; j < MAX_D; j++) nv[j] = 0.0;
-            const double lpn = logdensity_resident<P>(pp, tb, nv, sdt, sy, se, e2_0);
+        }
+        if (HELP) {
+            // every lane of the chain warps takes part in the hand-over protocol; `stepping` lanes evaluate
+            lpn = logdensity_assisted<P>(pp, tb, hs, stepping, nv, sy, se, e2_0, tick);
+            if (stepping && lpn != lpn) lpn = logdensity_resident<P>(pp, tb, nv, sdt, sy, se, e2_0);
+        } else if (stepping) {
+            lpn = logdensity_resident<P>(pp, tb, nv, sdt, sy, se, e2_0);
+        }
+        if (stepping) {
             // ---- Accept (steps.cpp:36-56)
             double alpha = (lpn - lp) / temp;
             double u = NAN;
@@ -497,14 +688,21 @@ static size_t pt_smem_bytes(int nyp, int d) {
 
 template <int P>
 static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t chol_stride, unsigned grid,
-                             cudaStream_t stream, const PTMulti& mm) {
+                             cudaStream_t stream, const PTMulti& mm, bool help) {
     size_t smem = pt_smem_bytes(mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0, pp.d);
     // always the same value (the residency rule keeps smem <= PT_SMEM_MAX): function attributes are process-wide,
     // and fits of different models launch this kernel concurrently from several host threads
     if (smem > PT_SMEM_MAX) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX);
+    if (help) {
+        smem += HelpShared<P>::doubles() * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_HELP_MAX);
+        if (e != cudaSuccess) return e;
+        pt_kernel<P, true><<<grid, PT_BLOCK * (1 + HELP_GROUPS), smem, stream>>>(sv, pp, chol_stride, mm);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    pt_kernel<P><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
+    pt_kernel<P, false><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
     return cudaGetLastError();
 }
 
@@ -598,10 +796,16 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
     // series resident in shared memory when it fits (<= 96 KiB keeps at least two blocks per SM)
     mm.resident = pt_smem_bytes(mm.enabled ? mm.max_nyp : sv.nyp, pp.d) <= PT_SMEM_MAX ? 1 : 0;
     pp.series_in_smem = mm.resident;
+    bool help = false;
     {
         // latency-bound regime (at most ~2 blocks per SM): pipelined loop; CARMA_PT_PIPE=0/1 overrides (measurements)
         const char* e = getenv("CARMA_PT_PIPE");
         pp.pipelined = e ? (e[0] == '1') : (grid <= 2u * 148u);
+        // at most one block per SM, series resident, one series: warp-specialised kernel (CARMA_PT_HELP=0/1 overrides)
+        const char* h = getenv("CARMA_PT_HELP");
+        const size_t help_bytes = ((size_t)HELP_RING * (2 * (p / 2) + 1) * PT_BLOCK + (size_t)p * PT_BLOCK + PT_BLOCK / 2 + 8) * sizeof(double);
+        const bool can = !mm.enabled && mm.resident && pp.ny >= 2 && pt_smem_bytes(sv.nyp, pp.d) + help_bytes <= PT_SMEM_HELP_MAX;
+        help = can && (h ? (h[0] == '1') : (grid <= 148u));
     }
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
@@ -612,13 +816,13 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
     if (!cuda_ok(cudaMemsetAsync(pp.status, 0, sizeof(int), st), "memset status")) return CARMA_ERR_CUDA;
     cudaError_t e;
     switch (p) {
-        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st, mm); break;
-        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st, mm); break;
-        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st, mm); break;
-        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st, mm); break;
-        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st, mm); break;
-        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st, mm); break;
-        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st, mm); break;
+        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st, mm, help); break;
         default: e = cudaErrorInvalidValue;
     }
     if (!cuda_ok(e, "pt_kernel launch")) return CARMA_ERR_CUDA;

@@ -653,3 +653,27 @@ def test_simulated_survey_other_model_kinds(C, O):
     chi2 = np.array(chi2)
     assert abs(chi2.mean() / 250.0 - 1.0) < 4.0 * np.sqrt(2.0 / (250.0 * 96.0))
     m.close()
+
+
+def test_pt_helper_warp_kernel_is_bit_identical_to_the_plain_kernel(C):
+    """Small launches run the warp-specialised PT kernel (producer warps compute the transition blocks, the chain warps
+    only the state recursion; hand-over through a shared-memory ring).  Same operations on the same values: samples,
+    log-posteriors, acceptance and exchange rates are bit-identical to the plain kernel, for one and for several
+    ensembles, odd and even orders, CAR(1) (no exchanges) and a series with a real root pair among the chains."""
+    import os
+    from carma_pack_b200 import synth
+    cases = [(C.KIND_CARMA, 5, 3, 270, 10, 1), (C.KIND_CARMA, 5, 3, 270, 10, 7), (C.KIND_CARP, 4, 0, 151, 6, 13),
+             (C.KIND_CARMA, 7, 2, 90, 12, 3), (C.KIND_CAR1, 1, 0, 64, 1, 5), (C.KIND_ZCARMA, 3, 0, 120, 4, 20),
+             (C.KIND_CARMA, 2, 1, 12, 3, 2)]
+    for kind, p, q, ny, ntemps, nens in cases:
+        t, y, e = synth.readme_series(max(ny, 2), 7 + ny)
+        s = C.Series(t, y, e)
+        out = {}
+        for mode in ("0", "1"):
+            os.environ["CARMA_PT_HELP"] = mode
+            out[mode] = s.pt_run(kind, p, q, nsamples=40, burnin=60, ntemps=ntemps, n_ensembles=nens, seed=77 + p)
+        os.environ.pop("CARMA_PT_HELP")
+        for k in ("samples", "logposts", "accept_rates", "exchange_rates"):
+            assert np.array_equal(out["0"][k], out["1"][k], equal_nan=True), (kind, p, q, ny, k)
+        assert np.all(np.isfinite(out["1"]["logposts"]))
+        s.close()
