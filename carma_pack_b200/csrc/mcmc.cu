@@ -58,6 +58,7 @@ struct PTParams {
     int ny;
     int series_in_smem;  // 1: sdt/sy/se of the log-density calls point into shared memory
     int pipelined;       // 1: software-pipelined filter loop (few warps per SM: latency bound)
+    int r_in_smem;       // helper mode: the Cholesky factors of the block's chains live in shared memory
     // device buffers
     const double* init;  // d values or nullptr
     double* samples;     // [n_ens][nsamples][d]
@@ -190,13 +191,19 @@ struct HelpShared {
     volatile int* skip;                              // [2]  1: no lane of warp w evaluates in this tick
     volatile int* produced;                          // [HELP_GROUPS][2]  steps (absolute count) produced so far
     volatile int* consumed;                          // [2]
-    static size_t doubles() { return (size_t)HELP_RING * NF * PT_BLOCK + (size_t)P * PT_BLOCK + PT_BLOCK / 2 + 8; }
+    volatile int* zready;                            // [2]  ticks whose random numbers are in zbuf
+    double* zbuf;                                    // [2 (tick parity)][ZROWS][PT_BLOCK]: t draws, accept and exchange uniforms
+    static constexpr int ZROWS = MAX_D + 2;
+    __host__ __device__ static size_t doubles() {
+        return (size_t)HELP_RING * NF * PT_BLOCK + (size_t)P * PT_BLOCK + PT_BLOCK / 2 + 8 + (size_t)2 * ZROWS * PT_BLOCK;
+    }
     __device__ void carve(double* base) {
         ring = base;
         par = ring + (size_t)HELP_RING * NF * PT_BLOCK;
         pari = (int*)(par + (size_t)P * PT_BLOCK);
         int* flags = pari + PT_BLOCK;
-        posted = flags; skip = flags + 2; produced = flags + 4; consumed = flags + 8;
+        posted = flags; skip = flags + 2; produced = flags + 4; consumed = flags + 8; zready = flags + 10;
+        zbuf = par + (size_t)P * PT_BLOCK + PT_BLOCK / 2 + 8;
     }
 };
 
@@ -285,10 +292,32 @@ __device__ __noinline__ double logdensity_assisted(const PTParams& pp, const Mat
 template <int P>
 __device__ __noinline__ void helper_loop(const PTParams& pp, const MathTab& tb, const HelpShared<P>& hs, int g, int w,
                                          const double* sdt, int nticks, bool sync_each_tick) {
-    constexpr int NS = P / 2, NF = HelpShared<P>::NF;
+    constexpr int NS = P / 2, NF = HelpShared<P>::NF, ZR = HelpShared<P>::ZROWS;
     const int lane = threadIdx.x & 31, t64 = w * 32 + lane;
     const int nadv = pp.ny - 1;
     const uint32_t da = smem_u32(sdt), ra = smem_u32(hs.ring) + 8u * (uint32_t)t64;
+    // the chain this lane serves (same numbering as pt_kernel)
+    const int T = pp.T, epb = PT_BLOCK / T, e_local = t64 / T, ci = t64 % T;
+    const unsigned long long ens = (unsigned long long)blockIdx.x * epb + e_local;
+    const bool chain_active = (e_local < epb) && (ens < pp.n_ens);
+    const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + ci);
+    // group 0 also draws the random numbers of the NEXT tick while the chain warp is still filtering: they are
+    // addressed by (seed, chain, iteration, slot), not consumed from a state, so they can be made ahead of time
+    auto draw_tick = [&](int tick) {
+        const int n = pp.order_mode == 0 ? tick - (T - 1 - ci) : tick;
+        if (chain_active && n >= 0 && n < pp.total_iters) {
+            double* zb = hs.zbuf + (size_t)(tick & 1) * ZR * PT_BLOCK + t64;
+            for (int j = 0; j < pp.d; j++) zb[(size_t)j * PT_BLOCK] = tdist_draw(pp.seed, chain, STREAM_PROPOSAL, (uint32_t)n, (uint32_t)j, pp.dof);
+            double u0, u1;
+            uniforms2(pp.seed, chain, STREAM_ACCEPT, (uint32_t)n, 0u, &u0, &u1);
+            zb[(size_t)MAX_D * PT_BLOCK] = u0;
+            uniforms2(pp.seed, chain, STREAM_EXCHANGE, (uint32_t)n, 0u, &u0, &u1);
+            zb[(size_t)(MAX_D + 1) * PT_BLOCK] = u0;
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); hs.zready[w] = tick + 1; }
+    };
+    if (g == 0) draw_tick(0);
     for (int e = 0; e < nticks; e++) {
         spin_until(&hs.posted[w], e + 1);
         if (!hs.skip[w]) {
@@ -327,6 +356,7 @@ __device__ __noinline__ void helper_loop(const PTParams& pp, const MathTab& tb, 
             __syncwarp();
             if (lane == 0) { __threadfence_block(); hs.produced[g * 2 + w] = base + nadv; }
         }
+        if (g == 0 && e + 1 < nticks) draw_tick(e + 1);
         if (sync_each_tick) { __syncthreads(); __syncthreads(); }
     }
 }
@@ -391,6 +421,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
     double* xth = sdt + 3 * (size_t)nyp + 2;           // [PT_BLOCK][d] exchange area
     double* xlp = xth + (size_t)PT_BLOCK * d;           // [PT_BLOCK]
     double* xu = xlp + PT_BLOCK;                        // [PT_BLOCK] exchange uniforms
+    double* xtemp = xu + PT_BLOCK;                      // [PT_BLOCK] temperature ladder (carmcmc.cpp:92-95), computed once
     double e2_0;
     MathTab tb;
     tb.load();  // ends with __syncthreads()
@@ -453,6 +484,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
 
     const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + i);
     const double temp = (T > 1) ? exp(log(pp.tmax) * (double)i / (double)(T - 1)) : 1.0;  // carmcmc.cpp:92-95
+    if (!is_helper && tid < T) xtemp[tid] = temp;   // threads 0..T-1 are the chains of the block's first ensemble: i == tid
 
     double th[MAX_D];
     double lp = -INFINITY;
@@ -460,8 +492,14 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
     for (int j = 0; j < MAX_D; j++) th[j] = 0.0;
     int naccept = 0, nx_try = 0, nx_acc = 0;
 
-    // ---- initial proposal Cholesky factor (carmcmc.cpp:127-136; diagonal, so R = sqrt(diag))
+    // ---- initial proposal Cholesky factor (carmcmc.cpp:127-136; diagonal, so R = sqrt(diag)).  Packed upper
+    // triangle, [entry][chain]: in HBM (L2-resident) for full launches, in shared memory in helper mode when it fits
+    // (a lone warp pays the full L2 latency on every one of the d(d+1)/2 dependent loads of the rank-1 update)
     double* R = pp.chol + gtid;
+    if (HELP && pp.r_in_smem) {
+        R = xtemp + PT_BLOCK + HelpShared<P>::doubles() + tid;
+        chol_stride = PT_BLOCK;
+    }
     if (active) {
         for (int j = 0; j < d; j++)
             for (int k = 0; k <= j; k++) R[(size_t)tri(k, j) * chol_stride] = 0.0;
@@ -475,8 +513,8 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
 
     HelpShared<P> hs{};
     if (HELP) {
-        hs.carve(xu + PT_BLOCK);
-        if (threadIdx.x < 10) ((int*)hs.posted)[threadIdx.x] = 0;   // posted[2], skip[2], produced[4], consumed[2]
+        hs.carve(xtemp + PT_BLOCK);
+        if (threadIdx.x < 12) ((int*)hs.posted)[threadIdx.x] = 0;   // posted[2], skip[2], produced[4], consumed[2], zready[2]
         __syncthreads();
         if (is_helper) {
             const int hw = (threadIdx.x - PT_BLOCK) >> 5;            // helper warp 0..3: group = hw >> 1, chain warp = hw & 1
@@ -508,11 +546,20 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         const bool stepping = active && n >= 0 && n < total;
         double z[MAX_D], sp[MAX_D], nv[MAX_D];
         double znorm2 = 0.0, lpn = -INFINITY;
+        double u_acc = 0.0, u_exch = 0.0;   // helper mode: the tick's uniforms, drawn ahead by a producer warp
+        if (HELP) spin_until(&hs.zready[tid >> 5], tick + 1);
         if (stepping) {
             // ---- AdaptiveMetro::DoStep (steps.cpp:60-107)
-            for (int j = 0; j < d; j++) {
-                z[j] = tdist_draw(pp.seed, chain, STREAM_PROPOSAL, (uint32_t)n, (uint32_t)j, pp.dof);
-                znorm2 += z[j] * z[j];
+            if (HELP) {
+                const double* zb = hs.zbuf + (size_t)(tick & 1) * HelpShared<P>::ZROWS * PT_BLOCK + tid;
+                for (int j = 0; j < d; j++) { z[j] = zb[(size_t)j * PT_BLOCK]; znorm2 += z[j] * z[j]; }
+                u_acc = zb[(size_t)MAX_D * PT_BLOCK];
+                u_exch = zb[(size_t)(MAX_D + 1) * PT_BLOCK];
+            } else {
+                for (int j = 0; j < d; j++) {
+                    z[j] = tdist_draw(pp.seed, chain, STREAM_PROPOSAL, (uint32_t)n, (uint32_t)j, pp.dof);
+                    znorm2 += z[j] * z[j];
+                }
             }
             for (int j = 0; j < d; j++) {  // chol_factor_.t() * unit_proposal
                 double s = 0.0;
@@ -537,8 +584,12 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
             if (!isfinite(alpha)) {
                 alpha = 0.0;
             } else {
-                double u1;
-                uniforms2(pp.seed, chain, STREAM_ACCEPT, (uint32_t)n, 0u, &u, &u1);
+                if (HELP) {
+                    u = u_acc;
+                } else {
+                    double u1;
+                    uniforms2(pp.seed, chain, STREAM_ACCEPT, (uint32_t)n, 0u, &u, &u1);
+                }
                 alpha = fmin(exp(alpha), 1.0);
                 if (u < alpha) { acc = true; naccept++; }
             }
@@ -574,8 +625,8 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
             }
             // exchange uniform of ExchangeStep(i) at this iteration (drawn unconditionally, steps.hpp:337)
             if (i > 0) {
-                double u0, u1;
-                uniforms2(pp.seed, chain, STREAM_EXCHANGE, (uint32_t)n, 0u, &u0, &u1);
+                double u0 = u_exch, u1;
+                if (!HELP) uniforms2(pp.seed, chain, STREAM_EXCHANGE, (uint32_t)n, 0u, &u0, &u1);
                 xu[tid] = u0;
             }
             // order_mode 0: chain 0 finished iteration n -> store before this tick's exchanges
@@ -602,8 +653,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
                     const int c = pp.order_mode == 0 ? s : T - s;
                     const int nc = pp.order_mode == 0 ? tick - (T - 1 - c) : tick;
                     if (nc < 0 || nc >= total) continue;
-                    const double tc = exp(log(pp.tmax) * (double)c / (double)(T - 1));
-                    const double tcm = exp(log(pp.tmax) * (double)(c - 1) / (double)(T - 1));
+                    const double tc = xtemp[c], tcm = xtemp[c - 1];
                     const double this_lp = xlp[base + c], other_lp = xlp[base + c - 1];
                     double a = 1.0 / tc * (other_lp - this_lp) + 1.0 / tcm * (this_lp - other_lp);
                     // std::min(exp(a), 1.0) keeps a NaN (steps.hpp:334-337 then sets alpha = 0); CUDA's fmin would
@@ -683,7 +733,7 @@ __global__ void start_value_kernel(SeriesView sv, PTParams pp, uint32_t chain0, 
 }
 
 static size_t pt_smem_bytes(int nyp, int d) {
-    return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 2 * PT_BLOCK) * sizeof(double);
+    return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 3 * PT_BLOCK) * sizeof(double);
 }
 
 template <int P>
@@ -695,6 +745,7 @@ static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t ch
     if (smem > PT_SMEM_MAX) return cudaErrorInvalidValue;
     if (help) {
         smem += HelpShared<P>::doubles() * sizeof(double);
+        if (pp.r_in_smem) smem += (size_t)pp.d * (pp.d + 1) / 2 * PT_BLOCK * sizeof(double);
         cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_HELP_MAX);
         if (e != cudaSuccess) return e;
         pt_kernel<P, true><<<grid, PT_BLOCK * (1 + HELP_GROUPS), smem, stream>>>(sv, pp, chol_stride, mm);
@@ -803,9 +854,12 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
         pp.pipelined = e ? (e[0] == '1') : (grid <= 2u * 148u);
         // at most one block per SM, series resident, one series: warp-specialised kernel (CARMA_PT_HELP=0/1 overrides)
         const char* h = getenv("CARMA_PT_HELP");
-        const size_t help_bytes = ((size_t)HELP_RING * (2 * (p / 2) + 1) * PT_BLOCK + (size_t)p * PT_BLOCK + PT_BLOCK / 2 + 8) * sizeof(double);
+        const size_t help_bytes = ((size_t)HELP_RING * (2 * (p / 2) + 1) * PT_BLOCK + (size_t)p * PT_BLOCK + PT_BLOCK / 2 + 8 +
+                                   (size_t)2 * (MAX_D + 2) * PT_BLOCK) * sizeof(double);
         const bool can = !mm.enabled && mm.resident && pp.ny >= 2 && pt_smem_bytes(sv.nyp, pp.d) + help_bytes <= PT_SMEM_HELP_MAX;
         help = can && (h ? (h[0] == '1') : (grid <= 148u));
+        const size_t r_bytes = (size_t)pp.d * (pp.d + 1) / 2 * PT_BLOCK * sizeof(double);
+        pp.r_in_smem = (help && pt_smem_bytes(sv.nyp, pp.d) + help_bytes + r_bytes <= PT_SMEM_HELP_MAX) ? 1 : 0;
     }
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
