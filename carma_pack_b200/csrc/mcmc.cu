@@ -70,6 +70,16 @@ struct PTParams {
     carma_pt_trace_rec_t* exch_trace;  // [n_ens][iters][T]
     double* proposals;                 // [n_ens][iters][T][d]
     int* status;                       // !=0 : a chain found no finite starting value
+    // time-sliced mode (slice_ticks > 0): the launch has fewer blocks ("workers") than block-sized groups of
+    // ensembles; a worker pulls (group, slice of ticks) units from a queue, slice-major, and the chains' state is
+    // parked in HBM between slices.  Keeps every SM sub-partition at the same number of resident warps when the
+    // number of groups is not a multiple of what the GPU holds, and any number of ensembles in ONE wave.
+    int slice_ticks;
+    unsigned n_groups;
+    int* slice_queue;                  // next unit
+    int* slice_done;                   // [n_groups] slices completed
+    double* slice_state;               // [MAX_D + 1][nthreads_total]: theta, log-posterior
+    int* slice_counts;                 // [3][nthreads_total]: accepted, exchanges tried, exchanges accepted
 };
 
 // multi light-curve mode: every block works on ONE curve of a ragged batch (its own series, prior and
@@ -409,9 +419,11 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
     const int T = pp.T, d = pp.d;
     const int epb = PT_BLOCK / T;
     const int e_local = tid / T, i = tid % T;
-    const size_t gtid = (size_t)blockIdx.x * PT_BLOCK + tid;
+    const bool sliced = !HELP && pp.slice_ticks > 0;
+    size_t gtid = (size_t)blockIdx.x * PT_BLOCK + tid;
     unsigned long long ens;
     bool active;
+    __shared__ int s_unit;
     const int nyp = mm.resident ? (mm.enabled ? mm.max_nyp : sv.nyp) : 0;
 
     // [ dt | y | e2n | exchange area ] (the math tables are static shared arrays)
@@ -482,9 +494,37 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         e2_0 = sv.e2_0;
     }
 
-    const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + i);
     const double temp = (T > 1) ? exp(log(pp.tmax) * (double)i / (double)(T - 1)) : 1.0;  // carmcmc.cpp:92-95
     if (!is_helper && tid < T) xtemp[tid] = temp;   // threads 0..T-1 are the chains of the block's first ensemble: i == tid
+    const int total = pp.total_iters;
+    const int nticks = pp.order_mode == 0 ? total + T - 1 : total;
+    const int n_slices = sliced ? (nticks + pp.slice_ticks - 1) / pp.slice_ticks : 1;
+
+  // ---- one pass per unit of work: the whole run of this block's ensembles, or (time-sliced mode) one slice of
+  // ticks of the group of ensembles pulled from the queue
+  for (;;) {
+    int tick_begin = 0, tick_end = nticks;
+    if (sliced) {
+        if (threadIdx.x == 0) s_unit = atomicAdd(pp.slice_queue, 1);
+        __syncthreads();
+        const unsigned unit = (unsigned)s_unit;
+        __syncthreads();
+        if (unit >= pp.n_groups * (unsigned)n_slices) break;
+        const unsigned grp = unit % pp.n_groups;
+        const int slice = (int)(unit / pp.n_groups);
+        tick_begin = slice * pp.slice_ticks;
+        tick_end = min(nticks, tick_begin + pp.slice_ticks);
+        gtid = (size_t)grp * PT_BLOCK + tid;
+        ens = (unsigned long long)grp * epb + e_local;
+        active = (e_local < epb) && (ens < pp.n_ens);
+        if (slice > 0) {
+            // the previous slice of this group was pulled n_groups units ago, normally long finished
+            if (threadIdx.x == 0) spin_until((volatile int*)(pp.slice_done + grp), slice);
+            __syncthreads();
+            __threadfence();
+        }
+    }
+    const uint32_t chain = (uint32_t)((pp.ens_offset + ens) * (unsigned long long)T + i);
 
     double th[MAX_D];
     double lp = -INFINITY;
@@ -500,16 +540,22 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         R = xtemp + PT_BLOCK + HelpShared<P>::doubles() + tid;
         chol_stride = PT_BLOCK;
     }
-    if (active) {
+    // sliced mode: another SM may have written this group's factor since this SM last read it -> bypass L1
+    auto rload = [&](const double* q) { return sliced ? __ldcg(q) : *q; };
+    if (active && tick_begin > 0) {
+        for (int j = 0; j < d; j++) th[j] = __ldcg(pp.slice_state + (size_t)j * chol_stride + gtid);
+        lp = __ldcg(pp.slice_state + (size_t)MAX_D * chol_stride + gtid);
+        naccept = __ldcg(pp.slice_counts + gtid);
+        nx_try = __ldcg(pp.slice_counts + chol_stride + gtid);
+        nx_acc = __ldcg(pp.slice_counts + 2 * chol_stride + gtid);
+    }
+    if (active && tick_begin == 0) {
         for (int j = 0; j < d; j++)
             for (int k = 0; k <= j; k++) R[(size_t)tri(k, j) * chol_stride] = 0.0;
         for (int j = 0; j < d; j++) R[(size_t)tri(j, j) * chol_stride] = 0.01;
         R[(size_t)tri(0, 0) * chol_stride] = sqrt(2.0 * pp.y_var_pop * pp.y_var_pop / (double)pp.ny);
         R[(size_t)tri(2, 2) * chol_stride] = sqrt(pp.y_var_pop / (double)pp.ny);
     }
-
-    const int total = pp.total_iters;
-    const int nticks = pp.order_mode == 0 ? total + T - 1 : total;
 
     HelpShared<P> hs{};
     if (HELP) {
@@ -524,7 +570,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
     }
 
     // ---- starting values (samplers.cpp:75-93)
-    if (active) {
+    if (active && tick_begin == 0) {
         bool ok = false;
         if (pp.init) {
             for (int j = 0; j < d; j++) th[j] = pp.init[j];
@@ -541,7 +587,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         if (!ok) atomicExch(pp.status, 1);
     }
 
-    for (int tick = 0; tick < nticks; tick++) {
+    for (int tick = tick_begin; tick < tick_end; tick++) {
         const int n = pp.order_mode == 0 ? tick - (T - 1 - i) : tick;
         const bool stepping = active && n >= 0 && n < total;
         double z[MAX_D], sp[MAX_D], nv[MAX_D];
@@ -563,7 +609,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
             }
             for (int j = 0; j < d; j++) {  // chol_factor_.t() * unit_proposal
                 double s = 0.0;
-                for (int k = 0; k <= j; k++) s += R[(size_t)tri(k, j) * chol_stride] * z[k];
+                for (int k = 0; k <= j; k++) s += rload(R + (size_t)tri(k, j) * chol_stride) * z[k];
                 sp[j] = s;
                 nv[j] = th[j] + s;
             }
@@ -611,13 +657,13 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
                 const double sign = (alpha < pp.target) ? -1.0 : 1.0;
                 for (int j = 0; j < d; j++) sp[j] = f * sp[j];
                 for (int k = 0; k < d; k++) {  // CholUpdateR1 (steps.cpp:111-131)
-                    double lkk = R[(size_t)tri(k, k) * chol_stride];
+                    double lkk = rload(R + (size_t)tri(k, k) * chol_stride);
                     double r = sqrt(lkk * lkk + sign * sp[k] * sp[k]);
                     double c = r / lkk;
                     double s = sp[k] / lkk;
                     R[(size_t)tri(k, k) * chol_stride] = r;
                     for (int j = k + 1; j < d; j++) {
-                        double lkj = (R[(size_t)tri(k, j) * chol_stride] + sign * s * sp[j]) / c;
+                        double lkj = (rload(R + (size_t)tri(k, j) * chol_stride) + sign * s * sp[j]) / c;
                         R[(size_t)tri(k, j) * chol_stride] = lkj;
                         sp[j] = c * sp[j] - s * lkj;
                     }
@@ -702,10 +748,23 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         }
     }
 
-    if (active) {
+    if (active && tick_end == nticks) {
         if (pp.accept_rates) pp.accept_rates[(size_t)ens * T + i] = total > 0 ? (double)naccept / (double)total : 0.0;
         if (pp.exchange_rates) pp.exchange_rates[(size_t)ens * T + i] = nx_try > 0 ? (double)nx_acc / (double)nx_try : 0.0;
     }
+    if (!sliced) break;
+    // ---- park the chains and publish the slice
+    if (active && tick_end < nticks) {
+        for (int j = 0; j < d; j++) pp.slice_state[(size_t)j * chol_stride + gtid] = th[j];
+        pp.slice_state[(size_t)MAX_D * chol_stride + gtid] = lp;
+        pp.slice_counts[gtid] = naccept;
+        pp.slice_counts[chol_stride + gtid] = nx_try;
+        pp.slice_counts[2 * chol_stride + gtid] = nx_acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(pp.slice_done + (gtid / PT_BLOCK), tick_end / pp.slice_ticks + (tick_end == nticks ? 1 : 0));
+  }
 }
 
 // One starting value per thread (chains chain0 .. chain0 + n - 1), the series read from global memory: the draw
@@ -734,6 +793,60 @@ __global__ void start_value_kernel(SeriesView sv, PTParams pp, uint32_t chain0, 
 
 static size_t pt_smem_bytes(int nyp, int d) {
     return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 3 * PT_BLOCK) * sizeof(double);
+}
+
+// Blocks of pt_kernel<P, false> one SM holds (registers + this launch's shared memory).
+template <int P>
+static int pt_blocks_per_sm(size_t smem) {
+    int nb = 0;
+    if (cudaFuncSetAttribute(pt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pt_kernel<P, false>, PT_BLOCK, smem) != cudaSuccess) return 0;
+    return nb;
+}
+
+static int pt_blocks_per_sm(int p, size_t smem) {
+    switch (p) {
+        case 1: return pt_blocks_per_sm<1>(smem);
+        case 2: return pt_blocks_per_sm<2>(smem);
+        case 3: return pt_blocks_per_sm<3>(smem);
+        case 4: return pt_blocks_per_sm<4>(smem);
+        case 5: return pt_blocks_per_sm<5>(smem);
+        case 6: return pt_blocks_per_sm<6>(smem);
+        case 7: return pt_blocks_per_sm<7>(smem);
+    }
+    return 0;
+}
+
+// How many worker blocks a time-sliced launch should use for `groups` block-sized groups of ensembles, or 0 to
+// launch one block per group.  Measured on B200 (scripts/pt_balance_probe.py, CARMA(5,3), ny = 1000): the time of
+// a tick depends on the LARGEST number of warps any SM sub-partition hosts, t(1) : t(2) : t(3) = 1 : 1.37 : 1.79
+// (two-warp blocks go to sub-partitions (0,1) and (2,3) alternately), so 683 groups on 148 SMs run at t(3)
+// although two thirds of the sub-partitions hold two warps.  With W = 148 c workers (c even: every sub-partition
+// holds c/2 warps) the run costs (groups / W) t(c/2).
+static unsigned pt_slice_workers(unsigned groups, int sms, int occ) {
+    if (occ < 1 || sms < 1) return 0;
+    auto t = [](int k) { return 0.58 + 0.42 * k + (k > 3 ? 0.1 * (k - 3) : 0.0); };   // relative; k = warps per sub-partition
+    double best;
+    if (groups <= (unsigned)(sms * occ)) {
+        const int b = (int)((groups + sms - 1) / sms);
+        best = t((b + 1) / 2);
+    } else {
+        // more groups than the GPU holds: later waves run at whatever occupancy is left
+        best = 0.0;
+        for (unsigned left = groups; left > 0;) {
+            const unsigned w = std::min(left, (unsigned)(sms * occ));
+            best += t((int)(((w + sms - 1) / sms + 1) / 2));
+            left -= w;
+        }
+    }
+    unsigned pick = 0;
+    for (int c = 2; c <= occ; c += 2) {
+        const unsigned w = (unsigned)(sms * c);
+        if (w >= groups) break;
+        const double cost = (double)groups / (double)w * t(c / 2) * 1.02;   // 2 % for the queue and the parked state
+        if (cost < best) { best = cost; pick = w; }
+    }
+    return pick;
 }
 
 template <int P>
@@ -863,20 +976,51 @@ static int pt_launch(carma_series_t s, carma_multi_series_t m, const CurveInfo* 
     }
     size_t nthreads = (size_t)grid * PT_BLOCK;
     size_t ntri = (size_t)pp.d * (pp.d + 1) / 2;
-    if (!scratch->reserve(ntri * nthreads * sizeof(double) + 16)) return CARMA_ERR_CUDA;
+    // time-sliced launch (one series, not in helper mode): CARMA_PT_SLICE=0 disables, =W forces W workers
+    unsigned workers = 0;
+    const int nticks = pp.order_mode == 0 ? pp.total_iters + pp.T - 1 : pp.total_iters;
+    if (!mm.enabled && !help && nticks >= 8) {
+        const char* e = getenv("CARMA_PT_SLICE");
+        if (e) {
+            workers = (unsigned)std::max(0, atoi(e));
+        } else {
+            int dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            workers = pt_slice_workers(grid, sms, pt_blocks_per_sm(p, pt_smem_bytes(mm.resident ? sv.nyp : 0, pp.d)));
+        }
+        if (workers >= grid) workers = 0;
+    }
+    // [ chol | status, queue | done[groups] | parked state | parked counters ]
+    const size_t off_flags = ntri * nthreads * sizeof(double);
+    const size_t off_done = off_flags + 16;
+    const size_t off_state = (off_done + (workers ? (size_t)grid * sizeof(int) : 0) + 15) & ~(size_t)15;
+    const size_t off_counts = off_state + (workers ? (size_t)(MAX_D + 1) * nthreads * sizeof(double) : 0);
+    const size_t bytes = off_counts + (workers ? 3 * nthreads * sizeof(int) : 0);
+    if (!scratch->reserve(bytes)) return CARMA_ERR_CUDA;
     pp.chol = (double*)scratch->p;
-    pp.status = (int*)((char*)scratch->p + ntri * nthreads * sizeof(double));
+    pp.status = (int*)((char*)scratch->p + off_flags);
     if (d_status_out) *d_status_out = pp.status;
-    if (!cuda_ok(cudaMemsetAsync(pp.status, 0, sizeof(int), st), "memset status")) return CARMA_ERR_CUDA;
+    if (!cuda_ok(cudaMemsetAsync(pp.status, 0, off_state - off_flags, st), "memset status")) return CARMA_ERR_CUDA;
+    unsigned launch_grid = grid;
+    if (workers) {
+        pp.slice_ticks = std::max(4, nticks / 32);
+        pp.n_groups = grid;
+        pp.slice_queue = pp.status + 1;
+        pp.slice_done = (int*)((char*)scratch->p + off_done);
+        pp.slice_state = (double*)((char*)scratch->p + off_state);
+        pp.slice_counts = (int*)((char*)scratch->p + off_counts);
+        launch_grid = workers;
+    }
     cudaError_t e;
     switch (p) {
-        case 1: e = launch_pt<1>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 2: e = launch_pt<2>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 3: e = launch_pt<3>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 4: e = launch_pt<4>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 5: e = launch_pt<5>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 6: e = launch_pt<6>(sv, pp, nthreads, grid, st, mm, help); break;
-        case 7: e = launch_pt<7>(sv, pp, nthreads, grid, st, mm, help); break;
+        case 1: e = launch_pt<1>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 2: e = launch_pt<2>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 3: e = launch_pt<3>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 4: e = launch_pt<4>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 5: e = launch_pt<5>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 6: e = launch_pt<6>(sv, pp, nthreads, launch_grid, st, mm, help); break;
+        case 7: e = launch_pt<7>(sv, pp, nthreads, launch_grid, st, mm, help); break;
         default: e = cudaErrorInvalidValue;
     }
     if (!cuda_ok(e, "pt_kernel launch")) return CARMA_ERR_CUDA;

@@ -677,3 +677,54 @@ def test_pt_helper_warp_kernel_is_bit_identical_to_the_plain_kernel(C):
             assert np.array_equal(out["0"][k], out["1"][k], equal_nan=True), (kind, p, q, ny, k)
         assert np.all(np.isfinite(out["1"]["logposts"]))
         s.close()
+
+
+def test_pt_time_sliced_launch_is_bit_identical_to_one_block_per_group(C):
+    """When the number of 64-chain groups is not what the GPU holds evenly, pt_kernel runs as W < groups worker blocks
+    that pull (group, slice of ticks) units from a queue and park the chains in HBM between slices.  The chains do
+    the same operations on the same values whichever worker runs a slice: samples, log-posteriors, acceptance and
+    exchange rates and the recorded accept/exchange traces are bit-identical to the one-block-per-group launch --
+    for few workers (every group migrates between SMs), one worker (fully sequential), more groups than workers
+    by one, adaptation running across slice boundaries, and both step orders."""
+    import os
+    from carma_pack_b200 import synth
+    cases = [(C.KIND_CARMA, 5, 3, 120, 10, 100, 0, (1, 7, 16)), (C.KIND_CARMA, 3, 1, 60, 4, 333, 1, (20,)),
+             (C.KIND_CAR1, 1, 0, 64, 1, 200, 0, (3,)), (C.KIND_ZCARMA, 4, 0, 80, 6, 45, 0, (4,))]
+    for kind, p, q, ny, ntemps, nens, order_mode, workers in cases:
+        t, y, e = synth.readme_series(ny, 11 + ny)
+        s = C.Series(t, y, e)
+        os.environ["CARMA_PT_SLICE"] = "0"
+        os.environ["CARMA_PT_HELP"] = "0"
+        ref = s.pt_run(kind, p, q, nsamples=30, burnin=50, ntemps=ntemps, n_ensembles=nens, seed=5 + p, order_mode=order_mode)
+        for w in workers:
+            os.environ["CARMA_PT_SLICE"] = str(w)
+            got = s.pt_run(kind, p, q, nsamples=30, burnin=50, ntemps=ntemps, n_ensembles=nens, seed=5 + p, order_mode=order_mode)
+            for k in ("samples", "logposts", "accept_rates", "exchange_rates"):
+                assert np.array_equal(ref[k], got[k], equal_nan=True), (kind, p, q, w, k)
+        os.environ.pop("CARMA_PT_SLICE")
+        os.environ.pop("CARMA_PT_HELP")
+        assert np.all(np.isfinite(ref["logposts"]))
+        s.close()
+    # the recorded traces too (small case), and the automatic choice on a launch larger than one wave of blocks
+    t, y, e = synth.readme_series(40, 3)
+    s = C.Series(t, y, e)
+    os.environ["CARMA_PT_HELP"] = "0"
+    os.environ["CARMA_PT_SLICE"] = "0"
+    a = s.pt_run(C.KIND_CARMA, 2, 1, nsamples=10, burnin=20, ntemps=3, n_ensembles=50, seed=9, record_trace=True)
+    os.environ["CARMA_PT_SLICE"] = "2"
+    b = s.pt_run(C.KIND_CARMA, 2, 1, nsamples=10, burnin=20, ntemps=3, n_ensembles=50, seed=9, record_trace=True)
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            if a[k].dtype.names:
+                for f in a[k].dtype.names:
+                    if f != "pad":
+                        assert np.array_equal(a[k][f], b[k][f], equal_nan=True), (k, f)
+            else:
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+    os.environ["CARMA_PT_SLICE"] = "0"
+    c0 = s.pt_run(C.KIND_CARMA, 2, 1, nsamples=5, burnin=20, ntemps=3, n_ensembles=21 * 1000, seed=9)
+    os.environ.pop("CARMA_PT_SLICE")
+    c1 = s.pt_run(C.KIND_CARMA, 2, 1, nsamples=5, burnin=20, ntemps=3, n_ensembles=21 * 1000, seed=9)   # 1,000 groups: automatic
+    os.environ.pop("CARMA_PT_HELP")
+    assert np.array_equal(c0["samples"], c1["samples"]) and np.array_equal(c0["exchange_rates"], c1["exchange_rates"])
+    s.close()
