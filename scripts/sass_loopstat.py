@@ -97,6 +97,22 @@ def main():
                     f.write("// loglik_batch_kernel<5>: %s time loop, one Kalman step (cuobjdump -sass)\n" % name)
                     for a, t in b:
                         f.write("/*%05x*/  %s ;\n" % (a, t))
+    # K3: the filter loops of logdensity_resident<5> (noinline, emitted inside pt_kernel<5, false>): all-conjugate and
+    # generic, each plain and software-pipelined (the pipelined pair runs on launches of <= 296 blocks)
+    obj3 = os.path.join(BUILD, "mcmc.cu.o")
+    fun3 = "_ZN5carma9pt_kernelILi5ELb0EEEvNS_10SeriesViewENS_8PTParamsEmNS_7PTMultiE"
+    ins3 = parse(disasm(obj3, fun3))
+    hot3 = sorted([b for b in loops(ins3, min_dfma=40) if sum(("LDS" in t) for _, t in b) >= 3], key=len)
+    out["k3"] = {"function": "pt_kernel<5, false> (logdensity_resident<5> inlined text)", "kernel_instructions_total": len(ins3),
+                 "filter_loops_by_size": [stats(b) for b in hot3]}
+    if hot3:
+        # the generic plain loop is what config 3 executes (a warp mixes chains with and without real root pairs)
+        base = stats(hot3[0])["fp64_instructions"]
+        pick = next((b for b in hot3 if stats(b)["fp64_instructions"] > base + 5), hot3[0])
+        with open(os.path.join(OUT, "r02_k3_loop_P5_generic.sass"), "w") as f:
+            f.write("// pt_kernel<5,false>: generic time loop of logdensity_resident<5>, one Kalman step (cuobjdump -sass)\n")
+            for a, t in pick:
+                f.write("/*%05x*/  %s ;\n" % (a, t))
     with open(os.path.join(OUT, "r02_sass_loop_counts.json"), "w") as f:
         json.dump(out, f, indent=1)
     for P, e in out["k1"].items():
@@ -105,6 +121,8 @@ def main():
         print("P=%s  all-conjugate: %d instr, %d FP64 (%d flops), model %d cycles | generic: %s instr, %s FP64" % (
             P, a["instructions"], a["fp64_instructions"], a["fp64_flops"], a["dispatch_cycle_model"],
             g.get("instructions"), g.get("fp64_instructions")))
+    print("K3 P=5 loops (instr, FP64, model cycles):", [(x["instructions"], x["fp64_instructions"], x["dispatch_cycle_model"])
+                                                        for x in out["k3"]["filter_loops_by_size"]])
 
 
 if __name__ == "__main__":
