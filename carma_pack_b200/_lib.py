@@ -12,6 +12,28 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CARMA_B200_LIB") or os.path.join(_HERE, "libcarma_b200.so")  # override: tuning builds
 
+
+def _point_at_bundled_nccl():
+    """The library loads NCCL lazily (carma_comm_* / carma_gather_summaries).  When this Python environment ships a
+    pip-bundled NCCL (the one torch links against), make that the copy that gets mapped, so that a later
+    `import torch` in the same process finds the symbols it needs behind the soname libnccl.so.2.  torch itself is not
+    imported here."""
+    if os.environ.get("CARMA_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CARMA_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001 - best effort: the system NCCL is the fallback
+        pass
+
+
+_point_at_bundled_nccl()
+
 KIND_CAR1, KIND_CARP, KIND_CARMA, KIND_ZCAR, KIND_ZCARMA = 0, 1, 2, 3, 4
 IGNORE_BOUNDS, LOGLIK_ONLY = 1, 2
 MAX_P = 7

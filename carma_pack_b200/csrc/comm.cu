@@ -8,6 +8,7 @@
 // loads on a box without NCCL; the entry points then return CARMA_ERR_CUDA with an explanatory message.  A host that
 // already owns an ncclComm_t (e.g. created next to torch.distributed) passes it straight to carma_gather_summaries;
 // a host without one bootstraps with carma_comm_unique_id / carma_comm_init_rank.
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -40,6 +41,13 @@ NcclApi& api() {
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
             a.lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
             if (a.lib) break;
+        }
+        // CARMA_NCCL_LIB: the library to map when none is loaded yet.  A process that imports torch LATER needs torch's
+        // bundled NCCL to be the one behind the soname libnccl.so.2 (libtorch_cuda.so binds to newer symbols than an
+        // older system NCCL exports); carma_pack_b200/_lib.py points this variable at the bundled copy when there is one.
+        if (!a.lib) {
+            const char* path = getenv("CARMA_NCCL_LIB");
+            if (path && path[0]) a.lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
         }
         if (!a.lib)
             for (const char* name : {"libnccl.so.2", "libnccl.so"}) {

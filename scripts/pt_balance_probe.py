@@ -14,7 +14,9 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 t, y, e = synth.readme_series(1000, 1000)
 s = C.Series(t, y, e)
 out = {"iterations": iters, "rows": []}
-for blocks in (148, 296, 444, 592, 683, 740, 888, 1000, 1366):
+groups = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (148, 296, 444, 592, 683, 740, 888, 1000, 1366)
+out["CARMA_PT_PIPE"] = os.environ.get("CARMA_PT_PIPE", "auto")
+for blocks in groups:
     n_ens = blocks * 6 if blocks not in (683, 1366) else (4096 if blocks == 683 else 8192)
     for slice_env in ("0", None, "592", "888"):
         if slice_env in ("592", "888") and blocks <= int(slice_env):

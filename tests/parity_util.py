@@ -13,6 +13,9 @@ import os
 import numpy as np
 
 RTOL = 1e-9
+# a row that misses RTOL must be within this factor of the oracle's own measured irreproducibility there (worst
+# observed on B200: 4.1, profiles/parity_report_gpu.json)
+NOISE_FACTOR = 20.0
 REPORT = []   # one dict per assert_logpost_parity call that had want_ld
 
 
@@ -53,7 +56,7 @@ def assert_logpost_parity(got, want, want_ld=None, rtol=RTOL, max_illcond_frac=0
            "median_rel_err": float(np.median(err / scale)) if err.size else 0.0,
            "allowed_frac": max_illcond_frac, "allowed_rows": max_illcond_rows}
     REPORT.append(rec)
-    really_bad = bad & (err > 50.0 * noise + tol)
+    really_bad = bad & (err > NOISE_FACTOR * noise + tol)
     assert not really_bad.any(), "%s: %d rows differ beyond tolerance and beyond the oracle's own noise floor: %s" % (
         what, really_bad.sum(), idx[really_bad][:10])
     assert bad.mean() <= max_illcond_frac, "%s: %.4f of rows needed the noise-floor criterion" % (what, bad.mean())
@@ -75,7 +78,7 @@ def ulp_shift(theta, k):
 def write_report(root):
     if not REPORT:
         return None
-    out = {"rtol": RTOL, "criterion": "err <= rtol*max(|lp|,1), else err <= 50 x measured oracle noise floor", "calls": REPORT,
+    out = {"rtol": RTOL, "criterion": "err <= rtol*max(|lp|,1), else err <= %g x measured oracle noise floor" % NOISE_FACTOR, "calls": REPORT,
            "total_noise_floor_rows": int(sum(r["noise_floor_rows"] for r in REPORT)),
            "total_rows": int(sum(r["rows"] for r in REPORT))}
     # the GPU suite and the CPU (host-compiled kernels) suite keep separate files
