@@ -646,6 +646,7 @@ int carma_series_destroy(carma_series_t s) {
     for (int k = 0; k < 2; k++) {
         s->slot_in[k].release(); s->slot_out[k].release();
         if (s->slot_stream[k]) cudaStreamDestroy(s->slot_stream[k]);
+        if (s->blk_stream[k]) cudaStreamDestroy(s->blk_stream[k]);
     }
     delete s;
     return CARMA_OK;
@@ -682,12 +683,29 @@ int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_pri
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
     size_t d = (size_t)model_dim(kind, p, q);
     if (!s->scratch_in.reserve(n * d * sizeof(double)) || !s->scratch_out.reserve(n * sizeof(double))) return CARMA_ERR_CUDA;
-    cudaStream_t st = 0;
-    if (!cuda_ok(cudaMemcpyAsync(s->scratch_in.p, theta, n * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
-    int rc = carma_loglik_batch_dev(s, kind, p, q, prior, n, (const double*)s->scratch_in.p, (double*)s->scratch_out.p, flags, st);
-    if (rc) return rc;
-    if (!cuda_ok(cudaMemcpyAsync(logpost, s->scratch_out.p, n * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
-    if (!cuda_ok(cudaStreamSynchronize(st), "loglik_batch sync")) return CARMA_ERR_CUDA;
+    // Large batches go as four pieces alternating over two streams, so that the copy of a piece overlaps the kernels of
+    // the pieces before it (pinned host memory; with pageable memory the copies are staged and nothing is lost).  Rows
+    // are independent and a row's arithmetic does not depend on its batch mates: same bits as one launch.
+    const size_t npieces = n >= 16384 ? 4 : 1;
+    if (npieces > 1)
+        for (int k = 0; k < 2; k++)
+            if (!s->blk_stream[k] && !cuda_ok(cudaStreamCreateWithFlags(&s->blk_stream[k], cudaStreamNonBlocking), "cudaStreamCreate")) return CARMA_ERR_CUDA;
+    const size_t per = ((n + npieces - 1) / npieces + 63) & ~(size_t)63;
+    for (size_t k = 0, r0 = 0; k < npieces && r0 < n; k++, r0 += per) {
+        const size_t nr = std::min(per, n - r0);
+        cudaStream_t st = npieces > 1 ? s->blk_stream[k & 1] : (cudaStream_t)0;
+        double* din = (double*)s->scratch_in.p + r0 * d;
+        double* dout = (double*)s->scratch_out.p + r0;
+        if (!cuda_ok(cudaMemcpyAsync(din, theta + r0 * d, nr * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
+        int rc = carma_loglik_batch_dev(s, kind, p, q, prior, nr, din, dout, flags, st);
+        if (rc) return rc;
+        if (!cuda_ok(cudaMemcpyAsync(logpost + r0, dout, nr * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
+    }
+    if (npieces > 1) {
+        if (!cuda_ok(cudaStreamSynchronize(s->blk_stream[0]), "loglik_batch sync") || !cuda_ok(cudaStreamSynchronize(s->blk_stream[1]), "loglik_batch sync")) return CARMA_ERR_CUDA;
+    } else if (!cuda_ok(cudaStreamSynchronize(0), "loglik_batch sync")) {
+        return CARMA_ERR_CUDA;
+    }
     return CARMA_OK;
 }
 

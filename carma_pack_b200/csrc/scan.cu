@@ -575,6 +575,16 @@ scan_sum_kernel(const ScanParams<P>* __restrict__ spp, const double* __restrict_
     if (threadIdx.x == 0) *out = sh[0] + spp->prm.logprior;
 }
 
+// Points folded per thread when the caller does not say (chunk <= 0).  Measured (scripts/scan_chunk_probe.py, one
+// CARMA(3,1) theta): ny = 1e5 is fastest at 16 (0.13 ms against 0.25 at 128), ny = 1e6 at 32..64 (0.20 against 0.28),
+// ny = 4e6 at 128: the two per-chunk passes are sequential in the chunk, so the chunk should be as short as still
+// leaves the aggregate scan small -- about 24,000 aggregates over all rows.
+static int scan_auto_chunk(size_t ny, size_t nrows) {
+    const size_t target = std::max<size_t>(24000 / std::max<size_t>(nrows, 1), 256);
+    const size_t c = (ny + target - 1) / target;
+    return (int)std::min<size_t>(std::max<size_t>(c, 16), 128);
+}
+
 // The scan passes for `nrows` models whose ScanParams are produced by `fill_params(sp)`; with `em` (nrows must be 1)
 // pass 3 also writes the per-point predictive mean / variance / state.
 template <int P, class FillParams>
@@ -582,7 +592,7 @@ static int scan_core(carma_series* s, int nrows, int chunk, cudaStream_t st, dou
                      FillParams fill_params, const double* d_y_override = nullptr) {
     SeriesView sv = s->view();
     if (d_y_override) sv.y = d_y_override;   // same times and errors, other values (conditional simulation)
-    if (chunk <= 0) chunk = 128;
+    if (chunk <= 0) chunk = scan_auto_chunk(sv.ny, (size_t)nrows);
     chunk = std::max(chunk, 2);
     // two scan levels of 256 cover 65,536 aggregates: longer series get longer chunks
     chunk = std::max(chunk, (int)((sv.ny + (SCAN_TILE * SCAN_TILE) - 1) / (SCAN_TILE * SCAN_TILE)));
@@ -677,7 +687,8 @@ int carma_loglik_scan_dev(carma_series_t s, int kind, int p, int q, const carma_
     const size_t d = (size_t)model_dim(kind, p, q);
     cudaStream_t st = (cudaStream_t)stream;
     // rows are processed in groups so that the per-row scratch stays below ~1 GiB (and grid.y <= 65535)
-    const size_t chunk_eff = chunk > 0 ? (size_t)std::max(chunk, 2) : 128;
+    if (chunk <= 0) chunk = scan_auto_chunk(s->ny, n);
+    const size_t chunk_eff = (size_t)std::max(chunk, 2);
     size_t per_row = ((size_t)s->ny / chunk_eff + 2) * (size_t)(4 * p * p + 3 * p + 1) * sizeof(double) * 5;
     size_t group = std::max<size_t>(1, std::min<size_t>(n, std::min<size_t>(4096, ((size_t)1 << 30) / std::max<size_t>(per_row, 1))));
     for (size_t i0 = 0; i0 < n; i0 += group) {

@@ -40,6 +40,7 @@ struct carma_series {
     // two pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
     carma::DevBuf slot_in[2], slot_out[2];
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    cudaStream_t blk_stream[2] = {nullptr, nullptr};   // the blocking batch call splits large batches over these
     carma::SeriesView view() const {
         carma::SeriesView v;
         v.dt = d_pack;
