@@ -217,6 +217,15 @@ struct HelpShared {
     }
 };
 
+// Barrier of the chain threads around the exchanges of a tick.  In the warp-specialised kernel only the PT_BLOCK chain
+// threads take part (named barrier with an explicit count): the producer warps are ordered by the hand-over flags
+// alone and never reach a block-wide barrier inside the tick loop.
+template <bool HELP>
+__device__ __forceinline__ void tick_barrier() {
+    if (HELP) asm volatile("bar.sync 1, %0;" ::"n"(PT_BLOCK) : "memory");
+    else __syncthreads();
+}
+
 __device__ __forceinline__ void spin_until(volatile int* flag, int target) {
     while ((int)(*flag - target) < 0) {
     }
@@ -301,7 +310,7 @@ __device__ __noinline__ double logdensity_assisted(const PTParams& pp, const Mat
 // producer side: one warp of group g serving chain warp w, for every tick of the run
 template <int P>
 __device__ __noinline__ void helper_loop(const PTParams& pp, const MathTab& tb, const HelpShared<P>& hs, int g, int w,
-                                         const double* sdt, int nticks, bool sync_each_tick) {
+                                         const double* sdt, int nticks) {
     constexpr int NS = P / 2, NF = HelpShared<P>::NF, ZR = HelpShared<P>::ZROWS;
     const int lane = threadIdx.x & 31, t64 = w * 32 + lane;
     const int nadv = pp.ny - 1;
@@ -367,7 +376,6 @@ __device__ __noinline__ void helper_loop(const PTParams& pp, const MathTab& tb, 
             if (lane == 0) { __threadfence_block(); hs.produced[g * 2 + w] = base + nadv; }
         }
         if (g == 0 && e + 1 < nticks) draw_tick(e + 1);
-        if (sync_each_tick) { __syncthreads(); __syncthreads(); }
     }
 }
 
@@ -564,7 +572,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
         __syncthreads();
         if (is_helper) {
             const int hw = (threadIdx.x - PT_BLOCK) >> 5;            // helper warp 0..3: group = hw >> 1, chain warp = hw & 1
-            helper_loop<P>(pp, tb, hs, hw >> 1, hw & 1, sdt, nticks, T > 1);
+            helper_loop<P>(pp, tb, hs, hw >> 1, hw & 1, sdt, nticks);
             return;
         }
     }
@@ -691,7 +699,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
                 for (int j = 0; j < d; j++) xth[(size_t)tid * d + j] = th[j];
                 xlp[tid] = lp;
             }
-            __syncthreads();
+            tick_barrier<HELP>();
             if (active && i == 0) {
                 const int base = tid;  // thread of chain 0 of this ensemble
                 for (int s = 1; s < T; s++) {
@@ -727,7 +735,7 @@ pt_kernel(SeriesView sv, PTParams pp_in, size_t chol_stride, PTMulti mm) {
                     xu[base + c] = sw ? 2.0 : 3.0;  // consumed marker: 2 = swapped, 3 = tried
                 }
             }
-            __syncthreads();
+            tick_barrier<HELP>();
             if (active) {
                 for (int j = 0; j < d; j++) th[j] = xth[(size_t)tid * d + j];
                 lp = xlp[tid];

@@ -16,6 +16,20 @@ m, v = s.filter(1.0, [-0.1 + 0.3j, -0.1 - 0.3j, -0.05], [1.0, 0.5, 0.0])
 qm, qv = s.predict(1.0, [-0.1 + 0.3j, -0.1 - 0.3j, -0.05], [1.0, 0.5, 0.0], [t[0] - 1, t[5] + 0.1, t[-1] + 3])
 r = s.pt_run(C.KIND_CARMA, 5, 3, 4, 4, ntemps=10, n_ensembles=7, seed=2, prior=pr, record_trace=True)
 r1 = s.pt_run(C.KIND_CAR1, 1, 0, 4, 4, ntemps=1, n_ensembles=3, seed=2)
+# the three launch shapes of the PT kernel: warp-specialised (default for small launches), plain, time-sliced
+shapes = {}
+for name, env in (("help", {"CARMA_PT_HELP": "1"}), ("plain", {"CARMA_PT_HELP": "0", "CARMA_PT_SLICE": "0"}),
+                  ("sliced", {"CARMA_PT_HELP": "0", "CARMA_PT_SLICE": "2"})):
+    if os.environ.get("SANITIZER_SKIP_HELP") and name == "help":
+        continue
+    os.environ.update(env)
+    shapes[name] = s.pt_run(C.KIND_CARMA, 5, 3, 6, 10, ntemps=10, n_ensembles=20, seed=5, prior=pr)
+    for k in env:
+        os.environ.pop(k)
+names = list(shapes)
+for a in names[1:]:
+    assert np.array_equal(shapes[names[0]]["samples"], shapes[a]["samples"]), a
+ysim = s.simulate(1.0, [-0.1 + 0.3j, -0.1 - 0.3j, -0.05], [1.0, 0.5, 0.0], [t[0] - 1, t[5] + 0.1, t[-1] + 3], npaths=3, seed=1)
 ts, ys, es, off = [], [], [], [0]
 for c in range(9):
     n = int(rng.integers(5, 60))
