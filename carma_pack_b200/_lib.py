@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
     "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
     "carma_simulate", "carma_starting_value", "carma_comm_unique_id", "carma_comm_init_rank", "carma_comm_destroy",
-    "carma_gather_summaries", "carma_gather_summaries_dev",
+    "carma_gather_summaries", "carma_gather_summaries_dev", "carma_derived_params", "carma_derived_params_dev",
 ]
 
 
@@ -153,6 +153,8 @@ def _load():
                                  ctypes.c_uint64, _sz, _dp]
     L.carma_starting_value.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Prior), ctypes.c_uint64,
                                        ctypes.c_uint32, ctypes.c_int, _dp, _dp]
+    L.carma_derived_params.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, _sz, _dp, _dp, ctypes.c_int]
+    L.carma_derived_params_dev.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, _sz, _vp, _vp, _vp]
     L.carma_comm_unique_id.argtypes = [ctypes.c_char_p]
     L.carma_comm_init_rank.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     L.carma_comm_destroy.argtypes = [_vp]
@@ -193,6 +195,23 @@ def device_count():
     n = ctypes.c_int(0)
     rc = lib.carma_device_count(ctypes.byref(n))
     return n.value if rc == 0 else 0
+
+
+def derived_params(kind, p, q, theta, prior=None, device=0):
+    """Posterior post-processing on the device (carma_derived_params): theta rows -> dict of ar_roots (complex, n x p),
+    ar_coefs (n x p+1, highest power first), ma_coefs (n x p, beta_0 = 1, zero beyond q), sigma (n), psd_width and
+    psd_centroid (n x p)."""
+    th = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    d = model_dim(kind, p, q)
+    if th.shape[1] != d:
+        raise ValueError("theta must have %d columns for this model, got %d" % (d, th.shape[1]))
+    n = th.shape[0]
+    out = np.empty((n, 6 * p + 2))
+    check(lib.carma_derived_params(kind, p, q, ctypes.byref(prior) if prior is not None else None, n, _ptr(th), _ptr(out),
+                                   device), "carma_derived_params")
+    return {"ar_roots": out[:, 0:2 * p:2] + 1j * out[:, 1:2 * p:2], "ar_coefs": out[:, 2 * p:3 * p + 1].copy(),
+            "ma_coefs": out[:, 3 * p + 1:4 * p + 1].copy(), "sigma": out[:, 4 * p + 1].copy(),
+            "psd_width": out[:, 4 * p + 2:5 * p + 2].copy(), "psd_centroid": out[:, 5 * p + 2:6 * p + 2].copy()}
 
 
 class Series:

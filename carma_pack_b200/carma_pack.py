@@ -421,10 +421,12 @@ class CarmaSample(MCMCSample):
     """MCMC samples of a CARMA(p,q) model with derived quantities (carma_pack.py:263-546)."""
 
     def __init__(self, time, y, ysig, sampler=None, q=0, filename=None, MLE=None, trace=None, logpost=None, p=None,
-                 series=None, prior=None):
+                 series=None, prior=None, postprocess="device"):
         """Reference signature (carma_pack.py:267): CarmaSample(time, y, ysig, sampler, q=0, filename=None,
         MLE=None) with `sampler` the object returned by run_mcmc_carma.  Alternatively pass trace/logpost
-        arrays.  As in the reference, p is taken from the trace width minus 3 minus q (so a caller that
+        arrays.  postprocess: "device" (default) derives roots / coefficients / sigma of every sample in one kernel
+        launch (carma_derived_params); "numpy" is the vectorised host twin kept as the cross-check (and for the
+        tests that run without a GPU).  As in the reference, p is taken from the trace width minus 3 minus q (so a caller that
         forgets q gets p = p_true + q_true, which the reference's own test relies on: testCarmcmc.py:96)."""
         if sampler is not None:
             trace = np.array([list(r) for r in sampler.getSamples()], dtype=float)
@@ -447,10 +449,15 @@ class CarmaSample(MCMCSample):
         self._samples["mu"] = trace[:, 2]
         self._samples["quad_coefs"] = np.exp(trace[:, 3:3 + p])
         self._trace = trace
-        self._ar_roots()
-        self._ar_coefs()
-        self._ma_coefs(trace)
-        self._sigma_noise()
+        if postprocess == "device":
+            self._derive_on_device(trace)
+        elif postprocess == "numpy":
+            self._ar_roots()
+            self._ar_coefs()
+            self._ma_coefs(trace)
+            self._sigma_noise()
+        else:
+            raise ValueError("postprocess must be 'device' or 'numpy'")
         # "loglik" of the reference = getLogDensity with SetMLE(True) for every stored sample: nsamples more filter runs
         # across the FFI (carma_pack.py:307-313).  SetMLE(True) only skips the prior-BOUNDS test; LogPrior is still added
         # (carpack.hpp:173, 180), and every stored sample lies inside the bounds, so that number IS the stored
@@ -487,6 +494,17 @@ class CarmaSample(MCMCSample):
         stored sample.  Only needed to audit the stored log-posteriors; CarmaSample itself does not call it."""
         kind = KIND_CARMA if self.q > 0 else KIND_CARP
         return self._series.loglik(kind, self.p, self.q, self._trace, prior=self._prior, flags=IGNORE_BOUNDS)
+
+    def _derive_on_device(self, trace):
+        """carma_pack.py:439-546 for all samples at once on the GPU: same dictionary entries as the numpy twin below."""
+        kind = KIND_CARMA if self.q > 0 else KIND_CARP
+        der = _lib.derived_params(kind, self.p, self.q, trace)
+        self._samples["ar_roots"] = der["ar_roots"]
+        self._samples["psd_width"] = der["psd_width"]
+        self._samples["psd_centroid"] = der["psd_centroid"]
+        self._samples["ar_coefs"] = der["ar_coefs"]
+        self._samples["ma_coefs"] = der["ma_coefs"][:, :self.q + 1]
+        self._samples["sigma"] = der["sigma"]
 
     def _ar_roots(self):  # carma_pack.py:439-467
         qc = self._samples["quad_coefs"]

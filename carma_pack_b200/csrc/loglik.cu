@@ -480,6 +480,100 @@ bool arrange_roots(const double* om, const double* ma, int p, double sigsqr, dou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Posterior post-processing (src/carmcmc/carma_pack.py:439-546): one thread per stored sample turns the
+// theta row into the derived quantities CarmaSample exposes -- AR roots, AR polynomial, normalised MA coefficients,
+// sigma of the driving noise, PSD widths and centroids -- with the formulas of CarmaSample._ar_roots / _ar_coefs /
+// _ma_coefs / _sigma_noise (IEEE division throughout; the same root, MA and variance code paths as transform_theta).
+// Row layout of `out` (width 6P + 2): [ roots (re, im) x P | ar_coefs P+1 (highest power first) | ma_coefs P (beta_0 = 1,
+// zero beyond q) | sigma | psd_width P | psd_centroid P ].
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(128) derived_params_kernel(int kind, int q, carma_prior_t pr, const double* __restrict__ theta,
+                                                             size_t n, double* __restrict__ out) {
+    constexpr double PI = 3.14159265358979323846;
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int d = model_dim(kind, P, q);
+    const double* th = theta + r * (size_t)d;
+    double* o = out + r * (size_t)(6 * P + 2);
+    cxd w[P];
+    if (kind == CARMA_KIND_CAR1) w[0] = cx(-exp(th[3]), 0.0);
+    else quad_roots_dev<P>(th + 3, P, w);
+    // AR polynomial prod (x - w_k), highest power first (numpy.poly)
+    cxd ac[P + 1];
+    ac[0] = cx(1.0, 0.0);
+#pragma unroll
+    for (int i = 1; i <= P; i++) ac[i] = cx(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < P; i++)
+#pragma unroll
+        for (int j = P; j >= 1; j--)
+            if (j <= i + 1) ac[j] = ac[j] - w[i] * ac[j - 1];
+    // MA coefficients (carpack.cpp:522-580, 687-698)
+    double ma[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) ma[i] = (i == 0) ? 1.0 : 0.0;
+    if (kind == CARMA_KIND_CARMA && q > 0) {
+        cxd rt[P], cf[P];
+#pragma unroll
+        for (int i = 0; i < P; i++) { rt[i] = cx(0, 0); cf[i] = cx(0, 0); }
+        quad_roots_dev<P>(th + 3 + P, q, rt);
+        cf[0] = cx(1.0, 0.0);
+        for (int i = 0; i < q; i++)
+            for (int j = i + 1; j >= 1; j--) cf[j] = cf[j] - rt[i] * cf[j - 1];
+        const double norm = cf[q].re;
+        for (int i = 0; i <= q; i++) ma[i] = cf[q - i].re / norm;
+    } else if (kind == CARMA_KIND_ZCARMA) {
+        const double x = th[3 + P];
+        const double kn = exp(x) / (1.0 + exp(x));
+        const double kappa = (pr.kappa_high - pr.kappa_low) * kn + pr.kappa_low;
+        double binom = 1.0;
+#pragma unroll
+        for (int i = 1; i < P; i++) {
+            binom = binom * (double)(P - i) / (double)i;
+            ma[i] = rint(binom) / pow(kappa, (double)i);
+        }
+    }
+    // Variance(w, beta, sigma = 1) (carpack.cpp:377-409) -> sigma^2 = var / Variance
+    cxd var_acc = cx(0, 0);
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        cxd s1 = cx(ma[P - 1], 0), s2 = cx(ma[P - 1], 0);
+        const cxd mw = -w[k];
+#pragma unroll
+        for (int l = P - 2; l >= 0; l--) {
+            s1 = s1 * w[k] + cx(ma[l], 0);
+            s2 = s2 * mw + cx(ma[l], 0);
+        }
+        cxd dp = cx(1, 0);
+#pragma unroll
+        for (int l = 0; l < P; l++)
+            if (l != k) dp = dp * ((w[l] - w[k]) * (conj(w[l]) + w[k]));
+        var_acc = var_acc + cdiv(s1 * s2, (-2.0 * w[k].re) * dp);
+    }
+    const double ysigma = th[0];
+    const double sigsqr = (kind == CARMA_KIND_CAR1) ? 2.0 * ysigma * ysigma * (-w[0].re) : ysigma * ysigma / var_acc.re;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+        o[2 * k] = w[k].re;
+        o[2 * k + 1] = w[k].im;
+        o[2 * P + (P + 1) + k] = ma[k];
+        o[4 * P + 2 + k] = -w[k].re / (2.0 * PI);
+        o[5 * P + 2 + k] = fabs(w[k].im) / (2.0 * PI);
+    }
+#pragma unroll
+    for (int k = 0; k <= P; k++) o[2 * P + k] = ac[k].re;
+    o[4 * P + 1] = sqrt(sigsqr);
+}
+
+template <int P>
+static cudaError_t launch_derived(int kind, int q, const carma_prior_t& pr, const double* d_theta, size_t n, double* d_out,
+                                  cudaStream_t st) {
+    derived_params_kernel<P><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kind, q, pr, d_theta, n, d_out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 FMA saturation micro-benchmark (roofline denominator measured on the same GPU)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
@@ -736,6 +830,52 @@ int carma_loglik_batch_wait(carma_series_t s, int slot) {
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
     if (!cuda_ok(cudaStreamSynchronize(s->slot_stream[slot]), "loglik_batch_wait")) return CARMA_ERR_CUDA;
     return CARMA_OK;
+}
+
+int carma_derived_params_dev(int kind, int p, int q, const carma_prior_t* prior, size_t n, const double* d_theta,
+                             double* d_out, void* stream) {
+    if ((!d_theta || !d_out) && n) { set_error("carma_derived_params_dev: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_derived_params_dev: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (kind == CARMA_KIND_ZCARMA && !prior) { set_error("carma_derived_params_dev: ZCARMA needs the prior (kappa bounds)"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    carma_prior_t pr{};
+    if (prior) pr = *prior;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    switch (p) {
+        case 1: e = launch_derived<1>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 2: e = launch_derived<2>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 3: e = launch_derived<3>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 4: e = launch_derived<4>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 5: e = launch_derived<5>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 6: e = launch_derived<6>(kind, q, pr, d_theta, n, d_out, st); break;
+        case 7: e = launch_derived<7>(kind, q, pr, d_theta, n, d_out, st); break;
+        default: e = cudaErrorInvalidValue;
+    }
+    if (!cuda_ok(e, "derived_params_kernel launch")) return CARMA_ERR_CUDA;
+    return CARMA_OK;
+}
+
+int carma_derived_params(int kind, int p, int q, const carma_prior_t* prior, size_t n, const double* theta, double* out,
+                         int device) {
+    if ((!theta || !out) && n) { set_error("carma_derived_params: null argument"); return CARMA_ERR_ARG; }
+    if (!valid_model(kind, p, q)) { set_error("carma_derived_params: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
+    if (n == 0) return CARMA_OK;
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return CARMA_ERR_CUDA;
+    const size_t d = (size_t)model_dim(kind, p, q), w = (size_t)(6 * p + 2);
+    double *d_th = nullptr, *d_o = nullptr;
+    if (!cuda_ok(cudaMalloc(&d_th, n * d * sizeof(double)), "cudaMalloc") || !cuda_ok(cudaMalloc(&d_o, n * w * sizeof(double)), "cudaMalloc")) {
+        cudaFree(d_th);
+        return CARMA_ERR_CUDA;
+    }
+    int rc = CARMA_ERR_CUDA;
+    if (cuda_ok(cudaMemcpy(d_th, theta, n * d * sizeof(double), cudaMemcpyHostToDevice), "H2D theta")) {
+        rc = carma_derived_params_dev(kind, p, q, prior, n, d_th, d_o, nullptr);
+        if (rc == CARMA_OK && !cuda_ok(cudaMemcpy(out, d_o, n * w * sizeof(double), cudaMemcpyDeviceToHost), "D2H derived")) rc = CARMA_ERR_CUDA;
+    }
+    cudaFree(d_th);
+    cudaFree(d_o);
+    return rc;
 }
 
 int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out) {

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CARMA_B200_ABI_VERSION 3
+#define CARMA_B200_ABI_VERSION 4
 
 enum {
     CARMA_OK = 0,
@@ -117,6 +117,17 @@ int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const car
 int carma_loglik_batch_wait(carma_series_t s, int slot);
 /* CARMA_Base::getLogPrior (src/include/carpack.hpp:221-225): host-side scalar helper. */
 int carma_log_prior(int kind, int p, const double* theta, const carma_prior_t* prior, double* out);
+
+/* ---- posterior post-processing ---------------------------------------------------------------
+ * Replaces the per-sample Python loops of CarmaSample._ar_roots / _ar_coefs / _ma_coefs / _sigma_noise
+ * (src/carmcmc/carma_pack.py:439-546): n theta rows (an MCMC trace) -> n rows of width 6p + 2,
+ *   [ AR roots (re, im) x p | AR polynomial coefficients p+1, highest power first | MA coefficients p (beta_0 = 1, zero
+ *     beyond q) | sigma of the driving noise | PSD widths p (-Re w / 2pi) | PSD centroids p (|Im w| / 2pi) ],
+ * one thread per row, no light curve needed.  prior: only its kappa bounds are read (ZCARMA); may be NULL otherwise. */
+int carma_derived_params(int kind, int p, int q, const carma_prior_t* prior, size_t n, const double* theta, double* out,
+                         int device);
+int carma_derived_params_dev(int kind, int p, int q, const carma_prior_t* prior, size_t n, const double* d_theta,
+                             double* d_out, void* stream);
 
 /* ---- maximum-likelihood fits from many starts ----------------------------------------------
  * Replaces the ntrials scipy L-BFGS-B runs of CarmaModel.get_mle / _get_mle_single / _carma_loglik

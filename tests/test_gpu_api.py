@@ -360,3 +360,62 @@ def test_device_simulate_matches_the_exact_gaussian_process_conditional(cm):
     assert np.all(np.abs(np.diag(C_) - 1.0) < 5.0 * np.sqrt(2.0 / n)), np.abs(np.diag(C_) - 1.0).max()
     off = C_ - np.diag(np.diag(C_))
     assert np.abs(off).max() < 5.0 / np.sqrt(n), np.abs(off).max()
+
+
+def test_device_post_processing_matches_reference_values_and_the_numpy_twin(cm, loglik_cases):
+    """carma_derived_params (one thread per stored sample) against (i) the values the REFERENCE's own CarmaSample code
+    gives for the same theta rows (tests/golden/derived_params.npz) and (ii) the vectorised numpy twin, for every golden
+    (p, q) family incl. real-pair roots; ZCARMA rows (free kappa) through the C ABI directly against the golden values;
+    and a 200,000-sample trace in one launch."""
+    import os
+    from conftest import GOLDEN, golden_case_names
+    from carma_pack_b200 import _lib as L
+    derived = dict(np.load(os.path.join(GOLDEN, "derived_params.npz")))
+    t, y, e = loglik_cases["t60"], loglik_cases["y60"], loglik_cases["ysig60"]
+    checked = zc = 0
+    names = list(golden_case_names(loglik_cases))
+    for name in names + [n for n in ("z5",) if n not in names]:
+        p, q = int(loglik_cases[name + "_p"]), int(loglik_cases[name + "_q"])
+        th = loglik_cases[name + "_theta"]
+        if th.shape[1] != 3 + p + q:
+            # ZCARMA (not a CarmaSample trace in the reference): theta carries kappa, the prior supplies its bounds;
+            # expected values from the closed forms (carpack.cpp:687-698) and the reference's carma_variance
+            from math import comb
+            from carma_pack_b200 import synth
+            s = L.Series(t, y, e)
+            pr = s.default_prior()
+            der = L.derived_params(L.KIND_ZCARMA, p, 0, th, prior=pr)
+            s.close()
+            tw = cm.CarmaSample(t, y, e, trace=th[:, :3 + p], logpost=np.zeros(th.shape[0]), p=p, q=0, postprocess="numpy")
+            np.testing.assert_allclose(der["ar_roots"], tw._samples["ar_roots"], rtol=1e-13)
+            kappa = (pr.kappa_high - pr.kappa_low) / (1.0 + np.exp(-th[:, 3 + p])) + pr.kappa_low
+            ma = np.array([[comb(p - 1, i) / k ** i for i in range(p)] for k in kappa])
+            np.testing.assert_allclose(der["ma_coefs"], ma, rtol=1e-12)
+            for r in range(th.shape[0]):
+                v1 = synth.carma_variance(1.0, der["ar_roots"][r], ma[r])
+                np.testing.assert_allclose(der["sigma"][r] ** 2, th[r, 0] ** 2 / v1, rtol=1e-9)
+            zc += 1
+            continue
+        want = derived[name + "_roots"]
+        if True:
+            lp = loglik_cases[name + "_logpost"]
+            dev = cm.CarmaSample(t, y, e, trace=th, logpost=lp, p=p, q=q)               # default: device
+            twin = cm.CarmaSample(t, y, e, trace=th, logpost=lp, p=p, q=q, postprocess="numpy")
+            assert dev._series_obj is None                                              # no light curve is uploaded for this
+            for k in ("ar_roots", "ar_coefs", "ma_coefs", "sigma", "psd_width", "psd_centroid"):
+                a, b = np.asarray(dev._samples[k]), np.asarray(twin._samples[k])
+                assert a.shape == b.shape or a.size == b.size, (name, k, a.shape, b.shape)
+                np.testing.assert_allclose(np.ravel(a), np.ravel(b), rtol=1e-11, atol=1e-300, err_msg="%s %s" % (name, k))
+            der = {"ar_roots": dev._samples["ar_roots"], "sigma": np.ravel(dev._samples["sigma"]),
+                   "ma_coefs": np.pad(dev._samples["ma_coefs"], ((0, 0), (0, p - dev._samples["ma_coefs"].shape[1])))}
+        np.testing.assert_allclose(der["ar_roots"], want, rtol=1e-13, atol=0, err_msg=name)
+        np.testing.assert_allclose(der["ma_coefs"], derived[name + "_ma"], rtol=1e-12, atol=1e-15, err_msg=name)
+        np.testing.assert_allclose(der["sigma"] ** 2, derived[name + "_sigsqr"], rtol=1e-10, err_msg=name)
+        checked += 1
+    assert checked >= 12 and zc >= 1
+    rng = np.random.default_rng(1)
+    big = np.tile(loglik_cases["c53_theta"][:1], (200000, 1)) + 1e-3 * rng.standard_normal((200000, 11))
+    d = L.derived_params(L.KIND_CARMA, 5, 3, big)
+    tw = cm.CarmaSample(t, y, e, trace=big[:500], logpost=np.zeros(500), p=5, q=3, postprocess="numpy")
+    np.testing.assert_allclose(d["sigma"][:500], np.ravel(tw._samples["sigma"]), rtol=1e-10)
+    assert np.all(np.isfinite(d["sigma"])) and d["ar_roots"].shape == (200000, 5)

@@ -25,7 +25,7 @@ def test_roots_ma_sigma_match_reference_post_processing(loglik_cases, derived):
             continue  # ZCARMA rows carry kappa: not a CarmaSample trace
         lp = loglik_cases[name + "_logpost"]
         # no GPU is touched: the device series is only created by predict / simulate / kalman_filter
-        cs = CarmaSample(t, y, e, trace=th, logpost=lp, p=p, q=q)
+        cs = CarmaSample(t, y, e, trace=th, logpost=lp, p=p, q=q, postprocess="numpy")
         assert cs._series_obj is None
         roots = cs._samples["ar_roots"]
         want = derived[name + "_roots"]
