@@ -51,7 +51,8 @@ EXPORTED_SYMBOLS = [
     "carma_pt_default_opts", "carma_pt_run", "carma_pt_run_dev", "carma_multi_pt_run",
     "carma_fp64_peak_tflops", "carma_philox_dev", "carma_tdist_dev", "carma_fastmath_dev",
     "carma_simulate", "carma_starting_value", "carma_comm_unique_id", "carma_comm_init_rank", "carma_comm_destroy",
-    "carma_gather_summaries", "carma_gather_summaries_dev", "carma_derived_params", "carma_derived_params_dev",
+    "carma_gather_summaries", "carma_gather_summaries_dev", "carma_derived_params", "carma_derived_params_dev", "carma_mle_batch_device",
+    "carma_mle_grid_device",
 ]
 
 
@@ -77,6 +78,14 @@ class PTOpts(ctypes.Structure):
                 ("target_rate", ctypes.c_double), ("gamma", ctypes.c_double), ("seed", ctypes.c_uint64),
                 ("ensemble_offset", ctypes.c_uint32), ("max_start_attempts", ctypes.c_int),
                 ("order_mode", ctypes.c_int), ("record_trace", ctypes.c_int)]
+
+
+class MLEJob(ctypes.Structure):   # carma_mle_job_t
+    _fields_ = [("kind", ctypes.c_int), ("p", ctypes.c_int), ("q", ctypes.c_int), ("flags", ctypes.c_uint),
+                ("prior", Prior), ("nstart", ctypes.c_size_t)]
+
+
+MAX_DIM = 17   # CARMA_MAX_DIM
 
 
 class MLEOpts(ctypes.Structure):
@@ -132,6 +141,9 @@ def _load():
     L.carma_mle_batch.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, pr, ctypes.c_uint, _sz, _dp, _dp, _dp,
                                   ctypes.POINTER(MLEOpts), _dp, _dp, ctypes.POINTER(ctypes.c_int),
                                   ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    L.carma_mle_batch_device.argtypes = L.carma_mle_batch.argtypes
+    L.carma_mle_grid_device.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(MLEJob), _dp, _dp, _dp, ctypes.POINTER(MLEOpts),
+                                        _dp, _dp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
     L.carma_multi_loglik_dev.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp,
                                          ctypes.c_uint, _vp]
     L.carma_multi_loglik.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.c_uint]
@@ -363,9 +375,11 @@ class Series:
         return res
 
     def mle_batch(self, kind, p, q, x0, lower, upper, prior=None, flags=0, maxiter=1000, history=8, gtol=1e-5,
-                  ftol=2.2e-9, fd_eps=1e-8, slot=0):
-        """Projected L-BFGS from every row of x0 in lock-step (carma_mle_batch): minimises -LogDensity over the
-        box [lower, upper].  Returns (x, f, nit, nfev).  Releases the GIL for the whole fit."""
+                  ftol=2.2e-9, fd_eps=1e-8, slot=0, on_device=False):
+        """Projected L-BFGS from every row of x0: minimises -LogDensity over the box [lower, upper].  on_device=False:
+        carma_mle_batch (host loop, all rows in lock-step, one launch per batch of trial points); on_device=True:
+        carma_mle_batch_device (the whole fit of a start inside one kernel, one warp per start).  Returns
+        (x, f, nit, nfev).  Releases the GIL for the whole fit."""
         d = model_dim(kind, p, q)
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         if x0.ndim != 2 or x0.shape[1] != d:
@@ -379,10 +393,47 @@ class Series:
         n = x0.shape[0]
         x, f = np.empty((n, d)), np.empty(n)
         nit, nfev = ctypes.c_int(0), ctypes.c_longlong(0)
-        check(lib.carma_mle_batch(self.handle, kind, p, q, ctypes.byref(prior), flags, n, _ptr(x0), _ptr(lo), _ptr(hi),
-                                  ctypes.byref(o), _ptr(x), _ptr(f), ctypes.byref(nit), ctypes.byref(nfev), slot),
-              "carma_mle_batch")
+        fn = lib.carma_mle_batch_device if on_device else lib.carma_mle_batch
+        check(fn(self.handle, kind, p, q, ctypes.byref(prior), flags, n, _ptr(x0), _ptr(lo), _ptr(hi),
+                 ctypes.byref(o), _ptr(x), _ptr(f), ctypes.byref(nit), ctypes.byref(nfev), slot),
+              "carma_mle_batch_device" if on_device else "carma_mle_batch")
         return x, f, nit.value, nfev.value
+
+    def mle_grid(self, jobs, maxiter=1000, history=8, gtol=1e-5, ftol=2.2e-9, fd_eps=1e-8, slot=0):
+        """Several models fitted in one launch (carma_mle_grid_device).  jobs: sequence of (kind, p, q, x0, lower, upper,
+        prior, flags), the last six as CarmaModel.mle_starts returns them.  Returns a list of (x, f, nit, nfev), one per job."""
+        nj = len(jobs)
+        cj = (MLEJob * max(nj, 1))()
+        lo = np.zeros((max(nj, 1), MAX_DIM))
+        hi = np.zeros((max(nj, 1), MAX_DIM))
+        xs, dims = [], []
+        for j, (kind, p, q, x0, lower, upper, prior, flags) in enumerate(jobs):
+            d = model_dim(kind, p, q)
+            x0 = np.ascontiguousarray(x0, dtype=np.float64)
+            if x0.ndim != 2 or x0.shape[1] != d:
+                raise ValueError("x0 of job %d must be (nstart, %d)" % (j, d))
+            lo[j, :d] = np.asarray(lower, dtype=np.float64).reshape(d)
+            hi[j, :d] = np.asarray(upper, dtype=np.float64).reshape(d)
+            cj[j].kind, cj[j].p, cj[j].q, cj[j].flags, cj[j].nstart = kind, p, q, flags, x0.shape[0]
+            cj[j].prior = self.default_prior() if prior is None else prior
+            xs.append(x0.reshape(-1))
+            dims.append((x0.shape[0], d))
+        xin = np.ascontiguousarray(np.concatenate(xs)) if xs else np.zeros(0)
+        xout = np.empty_like(xin)
+        fout = np.empty(sum(n for n, _ in dims))
+        nit = (ctypes.c_int * max(nj, 1))()
+        nfev = (ctypes.c_longlong * max(nj, 1))()
+        o = MLEOpts()
+        lib.carma_mle_default_opts(ctypes.byref(o))
+        o.maxiter, o.history, o.gtol, o.ftol, o.fd_eps = maxiter, history, gtol, ftol, fd_eps
+        check(lib.carma_mle_grid_device(self.handle, nj, cj, _ptr(xin), _ptr(lo), _ptr(hi), ctypes.byref(o), _ptr(xout),
+                                        _ptr(fout), nit, nfev, slot), "carma_mle_grid_device")
+        res, ox, of = [], 0, 0
+        for j, (n, d) in enumerate(dims):
+            res.append((xout[ox:ox + n * d].reshape(n, d).copy(), fout[of:of + n].copy(), int(nit[j]), int(nfev[j])))
+            ox += n * d
+            of += n
+        return res
 
     def pt_run_dev(self, kind, p, q, opts, n_ensembles, d_samples, d_logposts, prior, d_init=None, d_accept=None,
                    d_exchange=None, stream=0):

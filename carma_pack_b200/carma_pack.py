@@ -181,6 +181,7 @@ class CarmaModel(object):
         self.device = device
         self.mcmc_sample = None
         self._series = None
+        self.mle_optimizer = "device"   # "device": the fit of a start inside one kernel; "native": host loop; see get_mle
 
     @property
     def series(self):
@@ -260,13 +261,14 @@ class CarmaModel(object):
         return kind, x0, lo, hi, prior, flags
 
     def get_mle(self, p, q, ntrials=100, njobs=1, seed=None, maxiter=1000, trial_offset=0, series=None,
-                optimizer="native"):
+                optimizer=None):
         """Maximum-likelihood estimate from `ntrials` random starts (carma_pack.py:92-129), all trials
         in lock-step on the GPU.  `njobs` is accepted for API compatibility and ignored.  trial_offset:
         global index of the first trial (multi-GPU sharding: the starts of trial j do not depend on which
         rank runs it).  series: device series to use (choose_order gives each worker thread its own).
-        optimizer: "native" = carma_mle_batch (C++ host loop, no interpreter in the iteration);
-        "python" = the same algorithm in numpy (batched_lbfgs), kept as the cross-check."""
+        optimizer: "device" = carma_mle_batch_device (the whole fit inside one kernel, one warp per start);
+        "native" = carma_mle_batch (C++ host loop, one launch per batch of trial points);
+        "python" = the same algorithm in numpy (batched_lbfgs), kept as the cross-check.  None: self.mle_optimizer."""
         series = self.series if series is None else series
         if seed is None:
             seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
@@ -280,17 +282,22 @@ class CarmaModel(object):
             series.loglik_wait(0)
             return -out
 
-        if optimizer == "native":
-            x, f, nit, nfev = series.mle_batch(kind, p, q, x0, lo, hi, prior=prior, flags=flags, maxiter=maxiter)
+        if optimizer is None:
+            optimizer = self.mle_optimizer
+        if optimizer in ("native", "device"):
+            x, f, nit, nfev = series.mle_batch(kind, p, q, x0, lo, hi, prior=prior, flags=flags, maxiter=maxiter,
+                                               on_device=(optimizer == "device"))
         elif optimizer == "python":
             x, f, nit, nfev = batched_lbfgs(negloglik, x0, lo, hi, maxiter=maxiter)
         else:
-            raise ValueError("optimizer must be 'native' or 'python'")
+            raise ValueError("optimizer must be 'device', 'native' or 'python'")
+        return self._mle_result(x, f, nit, nfev)
+
+    @staticmethod
+    def _mle_result(x, f, nit, nfev):
         best = int(np.argmin(f))
-        mle = OptimizeResult(x=x[best], fun=float(f[best]), nit=nit, nfev=nfev, success=bool(np.isfinite(f[best])),
-                             message="batched projected L-BFGS, best of %d starts" % ntrials,
-                             all_x=x, all_fun=f)
-        return mle
+        return OptimizeResult(x=x[best], fun=float(f[best]), nit=nit, nfev=nfev, success=bool(np.isfinite(f[best])),
+                              message="batched projected L-BFGS, best of %d starts" % len(f), all_x=x, all_fun=f)
 
     def choose_order(self, pmax, qmax=None, pqlist=None, njobs=1, ntrials=100, seed=None, verbose=True, dist=None):
         """Choose (p,q) by minimising AICc over a grid of MLEs (carma_pack.py:131-192).
@@ -328,24 +335,36 @@ class CarmaModel(object):
         # workers than host cores only add contention
         import os
         nworkers = max(1, min(len(units), max(4, min(16, os.cpu_count() or 8))))
+        if os.environ.get("CARMA_ORDER_WORKERS"):
+            nworkers = max(1, min(len(units), int(os.environ["CARMA_ORDER_WORKERS"])))
         pool_series = [Series(self.time, self.y, self.ysig, device=self.device) for _ in range(nworkers)]
         import queue
         free = queue.Queue()
         for srs in pool_series:
             free.put(srs)
 
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0]) % (2 ** 62)
+
         def fit(unit):
             k, first, count = unit
             p, q = pqlist[k]
             srs = free.get()
             try:
-                return k, self.get_mle(p, q, ntrials=count, njobs=njobs, seed=None if seed is None else seed + k,
-                                       trial_offset=first, series=srs)
+                if self.mle_optimizer == "device":   # only the starting values here (short runs), the fits below
+                    return k, self.mle_starts(p, q, count, seed + k, trial_offset=first, series=srs)
+                return k, self.get_mle(p, q, ntrials=count, njobs=njobs, seed=seed + k, trial_offset=first, series=srs)
             finally:
                 free.put(srs)
 
         with ThreadPoolExecutor(max_workers=nworkers) as ex:
             local = dict(ex.map(fit, units))
+        if self.mle_optimizer == "device":
+            # every start of every model in ONE launch (carma_mle_grid_device): the device serves them from a queue,
+            # heaviest model first; separate launches per model do not overlap well (see mle_dev.cu)
+            ks = [u[0] for u in units]
+            fits = pool_series[0].mle_grid([(local[k][0],) + tuple(pqlist[k]) + tuple(local[k][1:]) for k in ks])
+            local = {k: self._mle_result(*r) for k, r in zip(ks, fits)}
         for srs in pool_series:
             srs.close()
         if world > 1:

@@ -122,6 +122,20 @@ static size_t k1_smem_bytes(int P, int ny) {
     return std::max(series, lu);
 }
 
+// the > 48 KiB opt-in for every order at once, once per device (cudaFuncSetAttribute waits for running kernels: see
+// OncePerDevice in series.h)
+template <int P>
+static cudaError_t k1_attr_from() {
+    cudaError_t e = cudaFuncSetAttribute(loglik_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    if constexpr (P < MAX_P) return k1_attr_from<P + 1>();
+    else return cudaSuccess;
+}
+static cudaError_t k1_attrs() {
+    static OncePerDevice once;
+    return once.run([] { return k1_attr_from<1>(); });
+}
+
 template <int P>
 static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsigned flags, const carma_prior_t& prior,
                              const double* d_theta, double* d_out, size_t n, cudaStream_t stream) {
@@ -130,7 +144,7 @@ static cudaError_t launch_k1(const SeriesView& sv, int kind, int q, int d, unsig
     if (smem > 48 * 1024) {
         // > 48 KiB of dynamic shared memory needs the opt-in (P = 7: 54,528 B).  Per device and always the same
         // value, so concurrent callers cannot disagree.
-        cudaError_t e = cudaFuncSetAttribute(loglik_batch_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = k1_attrs();
         if (e != cudaSuccess) return e;
     }
     loglik_batch_kernel<P><<<grid, K1_BLOCK, smem, stream>>>(sv, kind, q, d, flags, prior, d_theta, d_out, n);
@@ -625,17 +639,61 @@ bool cuda_ok(cudaError_t e, const char* what) {
     (void)cudaGetLastError();  // a reported (non-sticky) error must not resurface in a later, unrelated launch check
     return false;
 }
+// Device memory comes from the device's stream-ordered pool.  cudaMalloc / cudaFree synchronise with the work in flight
+// on the device: a series handle that allocated its scratch buffers for the first time while OTHER host threads had long
+// kernels running (concurrent model fits of choose_order) stalled behind them, and the fits ended up one after the
+// other (measured: 4.2 s cold against 1.2 s with pre-allocated buffers).  A first allocation now waits for nothing; a
+// buffer that has to GROW still waits for the device before the old block goes back to the pool, because asynchronous
+// entry points (carma_*_dev) may have work queued on it in streams this library does not own.
+static cudaStream_t alloc_stream() {
+    static std::mutex mu;
+    static cudaStream_t st[64] = {};
+    static bool pool_set[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!st[dev] && cudaStreamCreateWithFlags(&st[dev], cudaStreamNonBlocking) != cudaSuccess) st[dev] = nullptr;
+    if (!pool_set[dev]) {
+        if (getenv("CARMA_LMEM_MAX")) {
+            unsigned fl = 0;
+            cudaGetDeviceFlags(&fl);
+            cudaError_t fe = cudaSetDeviceFlags(fl | cudaDeviceLmemResizeToMax);
+            fprintf(stderr, "[carma] cudaSetDeviceFlags(LmemResizeToMax) -> %d\n", (int)fe);
+            (void)cudaGetLastError();
+        }
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;   // freed blocks stay in the pool: no trip to the OS, no implicit synchronisation
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_set[dev] = true;
+    }
+    return st[dev];
+}
+void* dev_alloc(size_t bytes, const char* what) {
+    void* q = nullptr;
+    cudaStream_t as = alloc_stream();
+    if (!as) return cuda_ok(cudaMalloc(&q, bytes), what) ? q : nullptr;
+    if (!cuda_ok(cudaMallocAsync(&q, bytes, as), what) || !cuda_ok(cudaStreamSynchronize(as), what)) return nullptr;
+    return q;
+}
+void dev_free(void* q) {
+    if (!q) return;
+    cudaStream_t as = alloc_stream();
+    if (!getenv("CARMA_FREE_NOSYNC")) cudaDeviceSynchronize();   // see above: what cudaFree did implicitly
+    if (!as || cudaFreeAsync(q, as) != cudaSuccess) cudaFree(q);
+}
 bool DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return true;
-    if (p) cudaFree(p);
-    p = nullptr;
+    if (p) dev_free(p);
     cap = 0;
-    if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(scratch)")) return false;
+    p = dev_alloc(bytes, "device allocation (scratch)");
+    if (!p) return false;
     cap = bytes;
     return true;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     cap = 0;
 }
@@ -724,9 +782,10 @@ int carma_series_create(const double* time, const double* y, const double* yerr,
         pack[2 * (size_t)s->nyp + i] = (i + 1 < ny) ? yerr[i + 1] * yerr[i + 1] : 0.0;
         pack[3 * (size_t)s->nyp + i] = time[i];
     }
-    if (!cuda_ok(cudaMalloc((void**)&s->d_pack, pack.size() * sizeof(double)), "cudaMalloc(series)")) { delete s; return CARMA_ERR_CUDA; }
+    s->d_pack = (double*)dev_alloc(pack.size() * sizeof(double), "device allocation (series)");
+    if (!s->d_pack) { delete s; return CARMA_ERR_CUDA; }
     if (!cuda_ok(cudaMemcpy(s->d_pack, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice), "cudaMemcpy(series)")) {
-        cudaFree(s->d_pack); delete s; return CARMA_ERR_CUDA;
+        dev_free(s->d_pack); delete s; return CARMA_ERR_CUDA;
     }
     *out = s;
     return CARMA_OK;
@@ -735,7 +794,7 @@ int carma_series_create(const double* time, const double* y, const double* yerr,
 int carma_series_destroy(carma_series_t s) {
     if (!s) return CARMA_OK;
     cudaSetDevice(s->device);
-    if (s->d_pack) cudaFree(s->d_pack);
+    if (s->d_pack) dev_free(s->d_pack);
     s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release(); s->scratch_state.release();
     for (int k = 0; k < 2; k++) {
         s->slot_in[k].release(); s->slot_out[k].release();

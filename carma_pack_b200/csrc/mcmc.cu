@@ -803,11 +803,31 @@ static size_t pt_smem_bytes(int nyp, int d) {
     return (3 * (size_t)nyp + 2 + (size_t)PT_BLOCK * d + 3 * PT_BLOCK) * sizeof(double);
 }
 
+// the dynamic shared memory opt-in of both kernel variants for every order at once, once per device:
+// cudaFuncSetAttribute waits for running kernels, so a launch of a new order arriving while other runs are in flight
+// (concurrent model fits draw their starts with short PT runs) would stall behind them (see OncePerDevice)
+template <int P>
+static cudaError_t pt_attr_from() {
+    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pt_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_HELP_MAX);
+    if (e != cudaSuccess) return e;
+    if constexpr (P < MAX_P) return pt_attr_from<P + 1>();
+    else return cudaSuccess;
+}
+static cudaError_t pt_attrs() {
+    static OncePerDevice once;
+    return once.run([] { return pt_attr_from<1>(); });
+}
+template <int P>
+static cudaError_t pt_plain_attr() { return pt_attrs(); }
+template <int P>
+static cudaError_t pt_help_attr() { return pt_attrs(); }
+
 // Blocks of pt_kernel<P, false> one SM holds (registers + this launch's shared memory).
 template <int P>
 static int pt_blocks_per_sm(size_t smem) {
     int nb = 0;
-    if (cudaFuncSetAttribute(pt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX) != cudaSuccess) return 0;
+    if (pt_plain_attr<P>() != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pt_kernel<P, false>, PT_BLOCK, smem) != cudaSuccess) return 0;
     return nb;
 }
@@ -867,12 +887,12 @@ static cudaError_t launch_pt(const SeriesView& sv, const PTParams& pp, size_t ch
     if (help) {
         smem += HelpShared<P>::doubles() * sizeof(double);
         if (pp.r_in_smem) smem += (size_t)pp.d * (pp.d + 1) / 2 * PT_BLOCK * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_HELP_MAX);
+        cudaError_t e = pt_help_attr<P>();
         if (e != cudaSuccess) return e;
         pt_kernel<P, true><<<grid, PT_BLOCK * (1 + HELP_GROUPS), smem, stream>>>(sv, pp, chol_stride, mm);
         return cudaGetLastError();
     }
-    cudaError_t e = cudaFuncSetAttribute(pt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM_MAX);
+    cudaError_t e = pt_plain_attr<P>();
     if (e != cudaSuccess) return e;
     pt_kernel<P, false><<<grid, PT_BLOCK, smem, stream>>>(sv, pp, chol_stride, mm);
     return cudaGetLastError();

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "../../include/carma_b200.h"
@@ -18,6 +19,27 @@ void set_error(const std::string& msg);
 bool cuda_ok(cudaError_t e, const char* what);
 
 // scratch device buffer that only grows
+// cudaFuncSetAttribute waits for running instances of the function: set per launch, it made kernels launched from
+// different host threads (concurrent model fits) run one after the other.  Attributes are per device and always get the
+// same value here, so each launch site sets them once per device: `static OncePerDevice once;` inside the (templated)
+// launch function, then once.run([] { return cudaFuncSetAttribute(...); }).
+struct OncePerDevice {
+    std::mutex mu;
+    bool done[64] = {};
+    cudaError_t err[64] = {};
+    template <class F>
+    cudaError_t run(F f) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return f();
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[dev]) { err[dev] = f(); done[dev] = true; }
+        return err[dev];
+    }
+};
+
+void* dev_alloc(size_t bytes, const char* what);   // stream-ordered pool allocation, ready on return (loglik.cu)
+void dev_free(void* p);
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;

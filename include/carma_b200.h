@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CARMA_B200_ABI_VERSION 4
+#define CARMA_B200_ABI_VERSION 5
 
 enum {
     CARMA_OK = 0,
@@ -63,6 +63,7 @@ enum {
 };
 
 #define CARMA_MAX_P 7
+#define CARMA_MAX_DIM (3 + 2 * CARMA_MAX_P)   /* >= the parameter count of every model: 3+p+q, 4+p (ZCARMA), 3 (CAR1) */
 
 /* prior / bounds of CARMA_Base::SetPrior (src/include/carpack.hpp:201-207) and the ZCARMA kappa
  * bounds (src/include/carpack.hpp:413-419) */
@@ -158,6 +159,30 @@ int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_
                     size_t nstart, const double* x0, const double* lower, const double* upper,
                     const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out, long long* nfev_out,
                     int slot);
+/* The same fits with the optimiser itself on the device (one kernel launch per call): a warp owns a start, its lanes
+ * evaluate the trial points of a round (the d difference points of a gradient, the step sizes of a backtracking
+ * round) concurrently, lane 0 runs the L-BFGS arithmetic.  Same algorithm, options and outputs as carma_mle_batch
+ * (history <= 8); an iteration costs one evaluation of latency instead of a launch, two copies and a synchronise, and
+ * no start waits for another.  nit_out: the largest iteration count over the starts. */
+int carma_mle_batch_device(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
+                           size_t nstart, const double* x0, const double* lower, const double* upper,
+                           const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out,
+                           long long* nfev_out, int slot);
+/* Several models fitted in ONE launch (choose_order, carma_pack.py:131-192: every (p,q) of the grid from `ntrials`
+ * starts): the starts of all jobs form one queue on the device, served heaviest model first, each start fitted by a
+ * warp exactly as carma_mle_batch_device fits it (a start's result does not depend on what else is in the launch).
+ * x0 / x_out: the jobs' rows one after the other, job j holding nstart_j rows of d_j doubles; f_out: nstart_j values
+ * per job in the same order; lower / upper: njobs rows of CARMA_MAX_DIM doubles (the first d_j used); nit_out /
+ * nfev_out: njobs entries (may be NULL). */
+typedef struct carma_mle_job {
+    int kind, p, q;
+    unsigned flags;
+    carma_prior_t prior;
+    size_t nstart;
+} carma_mle_job_t;
+int carma_mle_grid_device(carma_series_t s, int njobs, const carma_mle_job_t* jobs, const double* x0,
+                          const double* lower, const double* upper, const carma_mle_opts_t* opts, double* x_out,
+                          double* f_out, int* nit_out, long long* nfev_out, int slot);
 
 /* ---- multi light-curve batch (one theta per curve) ----------------------------------------
  * The reference loops over objects in Python; this is the survey-scale form of the same

@@ -25,7 +25,7 @@ def test_header_symbols_all_exported():
         assert hasattr(C._lib.lib, n), "libcarma_b200.so does not export %s" % n
     # and the python binding knows every one of them
     assert set(names) == set(C._lib.EXPORTED_SYMBOLS)
-    assert C._lib.lib.carma_abi_version() == 4
+    assert C._lib.lib.carma_abi_version() == 5
 
 
 def test_struct_layouts_match_header():

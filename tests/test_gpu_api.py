@@ -275,6 +275,55 @@ def test_native_optimizer_matches_numpy_twin(cm):
         model.series.mle_batch(cm.KIND_CARMA, 3, 1, np.zeros((2, 7)), -np.ones(7), np.ones(7), slot=5)
 
 
+def test_device_optimizer_matches_the_host_loop(cm):
+    """carma_mle_batch_device (the whole fit of a start inside one kernel, a warp per start) against carma_mle_batch
+    (host loop) from the same starts.  Same algorithm decision for decision; the trial points go through a different
+    build of the prologue, so low orders agree start by start and high orders (forward differences on flat, multi-modal
+    surfaces amplify rounding) agree in the best optimum and for the majority of starts."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(200, 11)
+    model = cm.CarmaModel(t, y, e)
+    for p, q, frac in ((1, 0, 0.95), (2, 0, 0.95), (3, 1, 0.85), (5, 2, 0.5)):
+        a = model.get_mle(p, q, ntrials=32, seed=21, optimizer="native")
+        b = model.get_mle(p, q, ntrials=32, seed=21, optimizer="device")
+        assert np.isfinite(a.fun) and np.isfinite(b.fun)
+        assert abs(a.fun - b.fun) < 1e-3 * max(1.0, abs(a.fun)), (p, q, a.fun, b.fun)
+        fa, fb = np.asarray(a.all_fun), np.asarray(b.all_fun)
+        both = (fa < 1e299) & (fb < 1e299)
+        assert both.sum() >= 24
+        close = np.abs(fa[both] - fb[both]) < 1e-4 * np.maximum(1.0, np.abs(fa[both]))
+        assert close.mean() >= frac, (p, q, close.mean())
+        # every device optimum is a genuine function value at a point inside the box
+        kind = cm.KIND_CAR1 if p == 1 else (cm.KIND_CARMA if q > 0 else cm.KIND_CARP)
+        flags = 0 if p == 1 else cm.IGNORE_BOUNDS
+        re = -model.series.loglik(kind, p, q, b.all_x[both], prior=model.series.default_prior(True), flags=flags)
+        np.testing.assert_allclose(re, fb[both], rtol=1e-9)
+        assert b.nfev > 0 and b.nit >= 1
+    # a start's fit does not depend on the other starts of the launch
+    kind, x0, lo, hi, prior, flags = model.mle_starts(3, 1, 16, seed=5)
+    xa, fa, _, _ = model.series.mle_batch(kind, 3, 1, x0, lo, hi, prior=prior, flags=flags, on_device=True)
+    xb, fb, _, _ = model.series.mle_batch(kind, 3, 1, x0[5:9], lo, hi, prior=prior, flags=flags, on_device=True)
+    np.testing.assert_array_equal(fa[5:9], fb)
+    np.testing.assert_array_equal(xa[5:9], xb)
+    with pytest.raises(cm.CarmaError):
+        model.series.mle_batch(kind, 3, 1, x0, lo, hi, prior=prior, flags=flags, history=9, on_device=True)
+    # several models in one launch (carma_mle_grid_device): every job's result equals its own single-model launch
+    jobs = [model.mle_starts(p, q, n, seed=40 + p) for p, q, n in ((1, 0, 5), (4, 2, 9), (2, 1, 12), (6, 0, 7), (3, 0, 3))]
+    jobs[-1] = (jobs[-1][0], jobs[-1][1][:0]) + tuple(jobs[-1][2:])   # a job without starts
+    pqs = ((1, 0), (4, 2), (2, 1), (6, 0), (3, 0))
+    grid = model.series.mle_grid([(j[0], p, q) + tuple(j[1:]) for j, (p, q) in zip(jobs, pqs)])
+    assert len(grid) == len(jobs)
+    for (kind, x0, lo, hi, prior, flags), (p, q), (xg, fg, nitg, nfevg) in zip(jobs, pqs, grid):
+        if x0.shape[0] == 0:
+            assert xg.shape == (0, x0.shape[1]) and fg.size == 0 and nitg == 0 and nfevg == 0
+            continue
+        x1, f1, nit1, nfev1 = model.series.mle_batch(kind, p, q, x0, lo, hi, prior=prior, flags=flags, on_device=True)
+        np.testing.assert_array_equal(xg, x1)
+        np.testing.assert_array_equal(fg, f1)
+        assert (nitg, nfevg) == (nit1, nfev1)
+    assert model.series.mle_grid([]) == []
+
+
 def test_fast_filter_and_predict_equal_the_general_complex_kernels(cm):
     """KalmanFilterp::Filter / Predict for conjugate-symmetric roots run in the real-half recursion (time-parallel
     forward filter + per-query coefficient pass resuming from stored states); the general complex kernels

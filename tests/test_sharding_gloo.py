@@ -116,6 +116,7 @@ def _choose_order_worker(rank, world, port, q):
         cp.CarmaModel.get_mle = _fake_get_mle
         t = np.arange(120.0)
         model = cp.CarmaModel(t, np.sin(t), np.full(t.size, 0.1))
+        model.mle_optimizer = "native"   # the per-model path, whose get_mle the stand-in replaces
         mle, pqlist, aicc = model.choose_order(4, ntrials=10, seed=1, verbose=False, dist=dist)
         q.put((rank, list(pqlist), list(aicc), float(mle.fun), np.asarray(mle.x).tolist(), (model.p, model.q)))
     finally:
@@ -132,6 +133,7 @@ def test_choose_order_sharded_over_two_ranks_equals_single_process():
         cp.CarmaModel.get_mle = _fake_get_mle
         t = np.arange(120.0)
         model = cp.CarmaModel(t, np.sin(t), np.full(t.size, 0.1))
+        model.mle_optimizer = "native"
         mle1, pq1, aicc1 = model.choose_order(4, ntrials=10, seed=1, verbose=False)
         best1 = (model.p, model.q)
     finally:
