@@ -654,13 +654,6 @@ static cudaStream_t alloc_stream() {
     std::lock_guard<std::mutex> lk(mu);
     if (!st[dev] && cudaStreamCreateWithFlags(&st[dev], cudaStreamNonBlocking) != cudaSuccess) st[dev] = nullptr;
     if (!pool_set[dev]) {
-        if (getenv("CARMA_LMEM_MAX")) {
-            unsigned fl = 0;
-            cudaGetDeviceFlags(&fl);
-            cudaError_t fe = cudaSetDeviceFlags(fl | cudaDeviceLmemResizeToMax);
-            fprintf(stderr, "[carma] cudaSetDeviceFlags(LmemResizeToMax) -> %d\n", (int)fe);
-            (void)cudaGetLastError();
-        }
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ull;   // freed blocks stay in the pool: no trip to the OS, no implicit synchronisation
@@ -680,7 +673,7 @@ void* dev_alloc(size_t bytes, const char* what) {
 void dev_free(void* q) {
     if (!q) return;
     cudaStream_t as = alloc_stream();
-    if (!getenv("CARMA_FREE_NOSYNC")) cudaDeviceSynchronize();   // see above: what cudaFree did implicitly
+    cudaDeviceSynchronize();   // see above: what cudaFree did implicitly
     if (!as || cudaFreeAsync(q, as) != cudaSuccess) cudaFree(q);
 }
 bool DevBuf::reserve(size_t bytes) {

@@ -1,5 +1,6 @@
 """choose_order(7) x 100 starts with the on-device optimiser: wall time against the number of concurrent model fits
-and with the series read from shared memory or from global memory (CARMA_MLE_SERIES_SMEM)."""
+and with the series read from shared memory or from global memory (CARMA_MLE_SERIES_SMEM, a switch that only the build
+of that experiment had; with one launch per model, as choose_order worked before carma_mle_grid_device)."""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
