@@ -49,4 +49,15 @@ tc = sim.curve(129)
 lo_, hi_ = np.full(7, -10.0), np.full(7, 10.0)
 xm, fm, nit, nfev = s.mle_batch(C.KIND_CARMA, 3, 1, synth.prior_draws(6, 3, 1, t, y, rng), lo_, hi_, prior=pr,
                                 flags=C.IGNORE_BOUNDS, maxiter=3)
-print("ok", np.isfinite(lp).mean(), lp2[:2], m[:2], qv, r["logposts"].shape, r1["logposts"].shape, lm[:3], rm["logposts"].shape, ls[:2], tc[0][:2], fm[:2], nit, nfev)
+# the on-device optimiser: one model, and a grid of models of different orders served from the queue in one launch
+xd, fd, nitd, nfevd = s.mle_batch(C.KIND_CARMA, 3, 1, synth.prior_draws(6, 3, 1, t, y, rng), lo_, hi_, prior=pr,
+                                  flags=C.IGNORE_BOUNDS, maxiter=3, on_device=True)
+grid_jobs = []
+for p_, q_, n_ in ((2, 0, 5), (5, 2, 9), (7, 6, 4), (1, 0, 3)):
+    kind_ = C.KIND_CAR1 if p_ == 1 else (C.KIND_CARMA if q_ else C.KIND_CARP)
+    d_ = C.model_dim(kind_, p_, q_)
+    x0_ = np.tile(np.array([1.0, 1.0, 0.0, np.log(0.1)]), (n_, 1)) if p_ == 1 else synth.prior_draws(n_, p_, q_, t, y, rng)
+    grid_jobs.append((kind_, p_, q_, x0_, np.full(d_, -10.0), np.full(d_, 10.0), pr, 0 if p_ == 1 else C.IGNORE_BOUNDS))
+grid = s.mle_grid(grid_jobs, maxiter=2)
+assert len(grid) == 4 and all(np.all(np.isfinite(g[0])) for g in grid)
+print("ok", np.isfinite(lp).mean(), lp2[:2], m[:2], qv, r["logposts"].shape, r1["logposts"].shape, lm[:3], rm["logposts"].shape, ls[:2], tc[0][:2], fm[:2], nit, nfev, fd[:2], nitd, nfevd, [g[2] for g in grid])

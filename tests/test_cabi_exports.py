@@ -45,6 +45,13 @@ def test_struct_layouts_match_header():
     # scipy L-BFGS-B defaults used by the reference's fits (minimize(..., method="L-BFGS-B") at carma_pack.py:250): pgtol 1e-5, factr*eps 2.2e-9, eps 1e-8
     assert (m.maxiter, m.history, m.max_backtrack) == (1000, 8, 25)
     assert (m.gtol, m.ftol, m.fd_eps) == (1e-5, 2.2e-9, 1e-8)
+    # carma_mle_job_t: 3 ints + flags, the prior, size_t nstart; CARMA_MAX_DIM = 3 + 2 * CARMA_MAX_P
+    assert ctypes.sizeof(C._lib.MLEJob) == 4 * 4 + 6 * 8 + 8 and C._lib.MLEJob.prior.offset == 16
+    hdr = open(os.path.join(ROOT, "include", "carma_b200.h")).read()
+    assert int(re.search(r"#define CARMA_MAX_P (\d+)", hdr).group(1)) * 2 + 3 == C._lib.MAX_DIM
+    # argument checks of the grid fit come before any CUDA call
+    assert C._lib.lib.carma_mle_grid_device(None, 0, None, None, None, None, None, None, None, None, None, 0) != 0
+    assert b"carma_mle_grid_device" in C._lib.lib.carma_last_error()
 
 
 def test_argument_validation_without_gpu():
