@@ -266,8 +266,9 @@ def run_ours(args, rank, world, local_rank):
     # H2D of the 65,536 x 11 theta block and D2H of the 65,536 results inside the timed region).
     # Two forms: the blocking call, and the two-slot pipelined call (copies of step k+1 overlap the kernel
     # of step k) which is what a host-driven caller evaluating batch after batch would use.
-    h_theta = [torch.from_numpy(th).pin_memory(), torch.from_numpy(th.copy()).pin_memory()]
-    h_outs = [torch.empty(NTHETA, dtype=torch.float64).pin_memory() for _ in range(2)]
+    NSLOT = 4   # CARMA_N_SLOTS: steps in flight; with two, the H2D of a step could not start before the step two back had been waited for
+    h_theta = [torch.from_numpy(th.copy()).pin_memory() for _ in range(NSLOT)]
+    h_outs = [torch.empty(NTHETA, dtype=torch.float64).pin_memory() for _ in range(NSLOT)]
     h_out = h_outs[0]
     lib = C._lib.lib
 
@@ -289,14 +290,26 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_pipelined(nsteps):
         for k in range(nsteps):
-            slot = k & 1
-            if k >= 2:
-                series.loglik_wait(slot)      # results of step k-2 are in h_outs[slot]; its buffers are free again
+            slot = k % NSLOT
+            if k >= NSLOT:
+                series.loglik_wait(slot)      # results of step k-NSLOT are in h_outs[slot]; its buffers are free again
             series.loglik_async(C.KIND_CARMA, P, Q, h_theta[slot].data_ptr(), h_outs[slot].data_ptr(), NTHETA, prior, slot)
-        series.loglik_wait(0)
-        series.loglik_wait(1)
+        for slot in range(NSLOT):
+            series.loglik_wait(slot)
 
-    e2e_pipelined(4)
+    e2e_pipelined(2 * NSLOT)
+    # the box's host-to-device rate for one step's theta block (pinned), to read the e2e figure against
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d_ms = []
+    d_scratch = torch.empty_like(d_theta)
+    for _ in range(5):
+        ev0.record()
+        d_scratch.copy_(h_theta[0].view_as(d_theta), non_blocking=True)
+        ev1.record()
+        ev1.synchronize()
+        h2d_ms.append(ev0.elapsed_time(ev1))
+    h2d_gbs = NTHETA * d * 8 / (float(np.median(h2d_ms)) * 1e-3) / 1e9
+    del d_scratch
     pipe_s = []
     for _ in range(E2E_REPEATS):
         if dist:
@@ -463,7 +476,7 @@ def run_ours(args, rank, world, local_rank):
             from carma_pack_b200 import synth
             t5, y5, e5 = synth.readme_series(500, 500)
             model = C.CarmaModel(t5, y5, e5, device=dev)
-            model.choose_order(2, ntrials=8, seed=1, verbose=False, dist=dist)   # warm-up: module load, series, streams
+            model.choose_order(7, ntrials=2, seed=1, verbose=False, dist=dist)   # warm-up: every order's kernels loaded, series, streams
             if dist:
                 dist.barrier()
             t0 = time.perf_counter()
@@ -572,7 +585,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": world * NTHETA * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": NTHETA * d * 8,
                     "d2h_bytes_per_step": NTHETA * 8,
-                    "api": "carma_loglik_batch_async/_wait: two-slot pipeline over pinned host buffers, K steps",
+                    "api": "carma_loglik_batch_async/_wait: %d-slot pipeline over pinned host buffers, K steps" % NSLOT, "slots": NSLOT,
+                    "h2d_gbs_this_box": h2d_gbs,
                     "repeats": E2E_REPEATS, "statistic": "median over repeats of the K-step region (max over ranks per repeat)",
                     "repeat_values": [world * NTHETA * K / x for x in pipe_s],
                     "blocking_call_value": world * NTHETA * K / e2e_block_s,

@@ -789,11 +789,12 @@ int carma_series_destroy(carma_series_t s) {
     cudaSetDevice(s->device);
     if (s->d_pack) dev_free(s->d_pack);
     s->scratch_in.release(); s->scratch_out.release(); s->scratch_misc.release(); s->scratch_state.release();
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < CARMA_N_SLOTS; k++) {
         s->slot_in[k].release(); s->slot_out[k].release();
         if (s->slot_stream[k]) cudaStreamDestroy(s->slot_stream[k]);
-        if (s->blk_stream[k]) cudaStreamDestroy(s->blk_stream[k]);
     }
+    for (int k = 0; k < 2; k++)
+        if (s->blk_stream[k]) cudaStreamDestroy(s->blk_stream[k]);
     delete s;
     return CARMA_OK;
 }
@@ -857,7 +858,7 @@ int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_pri
 
 int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
                              const double* theta, double* logpost, unsigned flags, int slot) {
-    if (!s || !prior || (!theta && n) || (!logpost && n) || slot < 0 || slot > 1) { set_error("carma_loglik_batch_async: bad argument"); return CARMA_ERR_ARG; }
+    if (!s || !prior || (!theta && n) || (!logpost && n) || slot < 0 || slot >= CARMA_N_SLOTS) { set_error("carma_loglik_batch_async: bad argument"); return CARMA_ERR_ARG; }
     if (!valid_model(kind, p, q)) { set_error("carma_loglik_batch_async: invalid (kind,p,q)"); return CARMA_ERR_ARG; }
     if (n == 0) return CARMA_OK;
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
@@ -877,7 +878,7 @@ int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const car
 }
 
 int carma_loglik_batch_wait(carma_series_t s, int slot) {
-    if (!s || slot < 0 || slot > 1) { set_error("carma_loglik_batch_wait: bad argument"); return CARMA_ERR_ARG; }
+    if (!s || slot < 0 || slot >= CARMA_N_SLOTS) { set_error("carma_loglik_batch_wait: bad argument"); return CARMA_ERR_ARG; }
     if (!s->slot_stream[slot]) return CARMA_OK;
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
     if (!cuda_ok(cudaStreamSynchronize(s->slot_stream[slot]), "loglik_batch_wait")) return CARMA_ERR_CUDA;

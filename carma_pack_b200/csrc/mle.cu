@@ -118,7 +118,7 @@ extern "C" int carma_mle_batch(carma_series_t s, int kind, int p, int q, const c
                                size_t nstart, const double* x0, const double* lower, const double* upper,
                                const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out,
                                long long* nfev_out, int slot) {
-    if (!s || !prior || !x0 || !lower || !upper || !x_out || !f_out || slot < 0 || slot > 1) {
+    if (!s || !prior || !x0 || !lower || !upper || !x_out || !f_out || slot < 0 || slot >= CARMA_N_SLOTS) {
         set_error("carma_mle_batch: bad argument");
         return CARMA_ERR_ARG;
     }

@@ -59,9 +59,9 @@ struct carma_series {
     std::vector<double> t, y, yerr;
     carma::SeriesStats st{};
     carma::DevBuf scratch_in, scratch_out, scratch_misc, scratch_state;
-    // two pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
-    carma::DevBuf slot_in[2], slot_out[2];
-    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    // pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
+    carma::DevBuf slot_in[CARMA_N_SLOTS], slot_out[CARMA_N_SLOTS];
+    cudaStream_t slot_stream[CARMA_N_SLOTS] = {};
     cudaStream_t blk_stream[2] = {nullptr, nullptr};   // the blocking batch call splits large batches over these
     carma::SeriesView view() const {
         carma::SeriesView v;

@@ -63,6 +63,7 @@ enum {
 };
 
 #define CARMA_MAX_P 7
+#define CARMA_N_SLOTS 4   /* pipeline slots of a series for the *_async / mle entry points */
 #define CARMA_MAX_DIM (3 + 2 * CARMA_MAX_P)   /* >= the parameter count of every model: 3+p+q, 4+p (ZCARMA), 3 (CAR1) */
 
 /* prior / bounds of CARMA_Base::SetPrior (src/include/carpack.hpp:201-207) and the ZCARMA kappa
@@ -109,8 +110,8 @@ int carma_loglik_batch_dev(carma_series_t s, int kind, int p, int q, const carma
 int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
                        const double* theta, double* logpost, unsigned flags);
 /* Pipelined form of carma_loglik_batch for callers that evaluate batch after batch from host memory
- * (optimisers, samplers driven from the host): enqueue H2D + kernel + D2H on one of two internal slots
- * (slot = 0 or 1, each with its own stream and device buffers) and return at once; the copies of one slot
+ * (optimisers, samplers driven from the host): enqueue H2D + kernel + D2H on one of CARMA_N_SLOTS internal slots
+ * (slot = 0 .. CARMA_N_SLOTS-1, each with its own stream and device buffers) and return at once; the copies of one slot
  * overlap the kernel of the other.  The host buffers must stay valid (and should be pinned) until
  * carma_loglik_batch_wait(s, slot) returns. */
 int carma_loglik_batch_async(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, size_t n,
@@ -136,7 +137,7 @@ int carma_derived_params_dev(int kind, int p, int q, const carma_prior_t* prior,
  * all nstart starts in lock-step, every function value of an iteration evaluated in one batched launch.
  * The objective is  -LogDensity(theta)  with `flags` (CARMA_IGNORE_BOUNDS = SetMLE(true), carma_pack.py:242).
  * lower/upper: d entries, +-infinity allowed.  Outputs: x_out[nstart][d], f_out[nstart] (1e300 where no finite
- * value was ever found); nit_out / nfev_out may be NULL.  slot: the stream slot of the series to use (0/1), so
+ * value was ever found); nit_out / nfev_out may be NULL.  slot: the stream slot of the series to use (0 .. CARMA_N_SLOTS-1), so
  * fits driven from different host threads on different series handles overlap on the GPU. */
 typedef struct carma_mle_opts {
     int maxiter;        /* 1000: L-BFGS-B stops on maxfun = 15000 evaluations, i.e. ~1000 finite-difference gradients at d = 14 */

@@ -32,7 +32,7 @@ def main():
     tag = sys.argv[1]
     src = os.path.join(ROOT, "gpurun_out")
     dst = os.path.join(ROOT, "profiles")
-    for name in ("k1", "pt", "k4", "scan"):
+    for name in ("k1", "pt", "k4", "scan", "mle"):
         path = os.path.join(src, "%s_%s_ncu_raw.csv" % (tag, name))
         if not os.path.exists(path):
             continue
