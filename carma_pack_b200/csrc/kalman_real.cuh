@@ -377,6 +377,84 @@ CARMA_HD void filter_span_any_pipelined(KalmanReal<P>& kf, LogLikAcc& acc, const
     else filter_span_pipelined<P, false>(kf, acc, prm, tb, src, len, nadv);
 }
 
+// K4's loop: every thread streams ITS OWN light curve from global memory.  With one 8-byte load per array and step the
+// 32 lanes of a warp touch 32 different sectors per load, four times per sector, and the loads of a step are issued one
+// step ahead only: ncu showed the warps waiting on them (long-scoreboard 5.0 stalls per issue, FP64 pipe 53 %).  Here a
+// thread fetches FOUR steps of an array with one 32-byte access (a whole sector: a quarter of the L1 wavefronts) and
+// the block after the current one is in flight while the current one is computed (prefetch distance 4 to 7 steps).
+// dt, y: the curve's arrays; E: its yerr^2 array UNSHIFTED (step i uses E[i + 1], the next point's variance).
+// A misaligned curve start is peeled with up to three scalar steps.  Same operations in the same order as
+// filter_span_impl: bitwise equal results.
+#ifdef __CUDACC__
+struct Dbl4 { double a, b, c, d; };
+__device__ __forceinline__ Dbl4 ldg4(const double* q) {   // q 32-byte aligned
+    Dbl4 v;
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.a), "=d"(v.b) : "l"(q));
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2 + 16];" : "=d"(v.c), "=d"(v.d) : "l"(q));
+#else
+    v.a = q[0]; v.b = q[1]; v.c = q[2]; v.d = q[3];
+#endif
+    return v;
+}
+template <int P, bool ALLC, class Tab>
+__device__ void filter_span_blocks(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
+                                   const double* __restrict__ dt, const double* __restrict__ y,
+                                   const double* __restrict__ E, int len) {
+    const int nadv = len - 1;
+    int since = 0;
+    auto step = [&](double dt_i, double y_i, double e_i) {
+        const double innov = (y_i - prm.mu) - kf.mean;
+        const double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+        kf.template advance<ALLC>(prm, tb, innov, inv, dt_i, e_i);
+    };
+    int i = 0;
+    const int head = min(nadv, (int)((4u - (unsigned)(((size_t)dt >> 3) & 3u)) & 3u));
+    for (; i < head; i++) step(dt[i], y[i], E[i + 1]);
+    since = head;
+    if (i + 4 <= nadv) {
+        Dbl4 cdt = ldg4(dt + i), cy = ldg4(y + i), cE = ldg4(E + i);
+        for (;;) {
+            const bool nx = i + 8 <= len;   // the next block lies inside this curve
+            Dbl4 ndt = cdt, ny_ = cy, nE = cE;
+            double e_last;
+            if (nx) {
+                ndt = ldg4(dt + i + 4); ny_ = ldg4(y + i + 4); nE = ldg4(E + i + 4);
+                e_last = nE.a;
+            } else {
+                e_last = E[i + 4];          // i + 4 <= nadv = len - 1
+            }
+            step(cdt.a, cy.a, cE.b);
+            step(cdt.b, cy.b, cE.c);
+            step(cdt.c, cy.c, cE.d);
+            step(cdt.d, cy.d, e_last);
+            i += 4;
+            since += 4;
+            if (since >= RENORM_EVERY - 8) { acc.renorm(since); since = 0; }
+            if (!nx || i + 4 > nadv) break;
+            cdt = ndt; cy = ny_; cE = nE;
+        }
+    }
+    for (; i < nadv; i++, since++) step(dt[i], y[i], E[i + 1]);
+    if (since) acc.renorm(since);
+    {   // the last point is only scored
+        const double innov = (y[len - 1] - prm.mu) - kf.mean;
+        const double inv = rcp_fast(kf.var);
+        acc.add(kf.var, innov, inv);
+        acc.renorm(1);
+    }
+}
+template <int P, class Tab>
+__device__ void filter_span_blocks_any(KalmanReal<P>& kf, LogLikAcc& acc, const RealParams<P>& prm, const Tab& tb,
+                                       const double* dt, const double* y, const double* E, int len) {
+    constexpr unsigned ALL = (P / 2 > 0) ? ((1u << (P / 2)) - 1u) : 0u;
+    const bool all_c = __all_sync(__activemask(), prm.cmask == ALL);
+    if (all_c) filter_span_blocks<P, true>(kf, acc, prm, tb, dt, y, E, len);
+    else filter_span_blocks<P, false>(kf, acc, prm, tb, dt, y, E, len);
+}
+#endif
+
 // Exact (slow) evaluation of the log-likelihood of one theta: the same recursion with one log() per point.
 // Only reached when LogLikAcc::bad was raised (var not a positive normal number somewhere).
 template <int P, class Src, class Tab>

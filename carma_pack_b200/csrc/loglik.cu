@@ -173,7 +173,9 @@ cudaError_t launch_loglik_batch(const SeriesView& sv, int kind, int p, int q, un
 constexpr int K4_BLOCK = 64;
 
 // GTAB: math tables read from global memory (default, see MathTabGlobal) instead of static shared memory
-template <int P, bool GTAB>
+// BLK4: the curve is fetched four steps per access with the next block in flight (filter_span_blocks); false: one
+// step per access, one step ahead (CARMA_K4_LOADS=scalar, kept for comparison)
+template <int P, bool GTAB, bool BLK4>
 __global__ void __launch_bounds__(K4_BLOCK)
 multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y, const double* __restrict__ e2,
                     const long long* __restrict__ off, size_t ncurves, double dt_max, int kind, int q, int d, unsigned flags,
@@ -201,7 +203,8 @@ multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y,
     acc.init();
     // e2 of the NEXT point is needed at step i: pass the array shifted by one
     const SeriesPtr src{dt + o0, y + o0, e2 + o0 + 1};
-    filter_span_any<P, true>(kf, acc, prm, tb, src, ny, ny - 1);
+    if (BLK4) filter_span_blocks_any<P>(kf, acc, prm, tb, dt + o0, y + o0, e2 + o0, ny);
+    else filter_span_any<P, true>(kf, acc, prm, tb, src, ny, ny - 1);
     out[c] = (acc.bad() ? loglik_exact_slow<P>(prm, tb, src, ny, e2[o0]) : acc.value()) + prm.logprior;
 }
 
@@ -211,13 +214,13 @@ cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, in
     int d = model_dim(kind, p, q);
     unsigned grid = (unsigned)((m->ncurves + K4_BLOCK - 1) / K4_BLOCK);
     static const bool smem_tab = [] { const char* e = getenv("CARMA_K4_TABLES"); return e && !strcmp(e, "smem"); }();
+    static const bool scalar_loads = [] { const char* e = getenv("CARMA_K4_LOADS"); return e && !strcmp(e, "scalar"); }();
+#define LAUNCH_K4_AS(PP, GT, B4)                                                                                      \
+    multi_loglik_kernel<PP, GT, B4><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves,    \
+                                                                   m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out)
 #define LAUNCH_K4(PP)                                                                                                 \
-    if (smem_tab)                                                                                                     \
-        multi_loglik_kernel<PP, false><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves, \
-                                                                      m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out); \
-    else                                                                                                              \
-        multi_loglik_kernel<PP, true><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves,  \
-                                                                     m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out)
+    if (smem_tab) { if (scalar_loads) LAUNCH_K4_AS(PP, false, false); else LAUNCH_K4_AS(PP, false, true); }           \
+    else { if (scalar_loads) LAUNCH_K4_AS(PP, true, false); else LAUNCH_K4_AS(PP, true, true); }
     switch (p) {
         case 1: LAUNCH_K4(1); break;
         case 2: LAUNCH_K4(2); break;
