@@ -380,7 +380,7 @@ CARMA_HD void filter_span_any_pipelined(KalmanReal<P>& kf, LogLikAcc& acc, const
 // K4's loop: every thread streams ITS OWN light curve from global memory.  With one 8-byte load per array and step the
 // 32 lanes of a warp touch 32 different sectors per load, four times per sector, and the loads of a step are issued one
 // step ahead only: ncu showed the warps waiting on them (long-scoreboard 5.0 stalls per issue, FP64 pipe 53 %).  Here a
-// thread fetches FOUR steps of an array with one 32-byte access (a whole sector: a quarter of the L1 wavefronts) and
+// thread fetches FOUR steps of an array with one 256-bit access (a whole sector: a quarter of the L1 wavefronts) and
 // the block after the current one is in flight while the current one is computed (prefetch distance 4 to 7 steps).
 // dt, y: the curve's arrays; E: its yerr^2 array UNSHIFTED (step i uses E[i + 1], the next point's variance).
 // A misaligned curve start is peeled with up to three scalar steps.  Same operations in the same order as
@@ -390,8 +390,8 @@ struct Dbl4 { double a, b, c, d; };
 __device__ __forceinline__ Dbl4 ldg4(const double* q) {   // q 32-byte aligned
     Dbl4 v;
 #ifdef __CUDA_ARCH__
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.a), "=d"(v.b) : "l"(q));
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2 + 16];" : "=d"(v.c), "=d"(v.d) : "l"(q));
+    // one 256-bit access per sector (sm_100); the curve is read exactly once, so it does not need a line in L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(q));
 #else
     v.a = q[0]; v.b = q[1]; v.c = q[2]; v.d = q[3];
 #endif

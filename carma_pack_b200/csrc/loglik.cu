@@ -213,8 +213,16 @@ cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, in
                                 cudaStream_t stream) {
     int d = model_dim(kind, p, q);
     unsigned grid = (unsigned)((m->ncurves + K4_BLOCK - 1) / K4_BLOCK);
-    static const bool smem_tab = [] { const char* e = getenv("CARMA_K4_TABLES"); return e && !strcmp(e, "smem"); }();
     static const bool scalar_loads = [] { const char* e = getenv("CARMA_K4_LOADS"); return e && !strcmp(e, "scalar"); }();
+    // math tables: static shared arrays with the block loads (the curve no longer lives in L1 between steps, so the
+    // 4.6 kB per block are free: survey 1.27 -> 1.41e8 curves/s); global memory with the scalar loads, where shared
+    // tables cost the survey 10 % of L1 hits.  CARMA_K4_TABLES=smem|global overrides.
+    static const bool smem_tab = [] {
+        const char* e = getenv("CARMA_K4_TABLES");
+        if (e && !strcmp(e, "smem")) return true;
+        if (e && !strcmp(e, "global")) return false;
+        return !scalar_loads;
+    }();
 #define LAUNCH_K4_AS(PP, GT, B4)                                                                                      \
     multi_loglik_kernel<PP, GT, B4><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves,    \
                                                                    m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out)
@@ -796,7 +804,7 @@ int carma_series_destroy(carma_series_t s) {
         s->slot_in[k].release(); s->slot_out[k].release();
         if (s->slot_stream[k]) cudaStreamDestroy(s->slot_stream[k]);
     }
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 4; k++)
         if (s->blk_stream[k]) cudaStreamDestroy(s->blk_stream[k]);
     delete s;
     return CARMA_OK;
@@ -833,17 +841,18 @@ int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_pri
     if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return CARMA_ERR_CUDA;
     size_t d = (size_t)model_dim(kind, p, q);
     if (!s->scratch_in.reserve(n * d * sizeof(double)) || !s->scratch_out.reserve(n * sizeof(double))) return CARMA_ERR_CUDA;
-    // Large batches go as four pieces alternating over two streams, so that the copy of a piece overlaps the kernels of
-    // the pieces before it (pinned host memory; with pageable memory the copies are staged and nothing is lost).  Rows
-    // are independent and a row's arithmetic does not depend on its batch mates: same bits as one launch.
+    // Large batches go as four pieces on four streams, so that the copy of a piece overlaps the kernels of the pieces
+    // before it and the four kernels share the SMs like one launch (pinned host memory; with pageable memory the copies
+    // are staged and nothing is lost).  Rows are independent and a row's arithmetic does not depend on its batch mates:
+    // same bits as one launch.
     const size_t npieces = n >= 16384 ? 4 : 1;
     if (npieces > 1)
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < 4; k++)
             if (!s->blk_stream[k] && !cuda_ok(cudaStreamCreateWithFlags(&s->blk_stream[k], cudaStreamNonBlocking), "cudaStreamCreate")) return CARMA_ERR_CUDA;
     const size_t per = ((n + npieces - 1) / npieces + 63) & ~(size_t)63;
     for (size_t k = 0, r0 = 0; k < npieces && r0 < n; k++, r0 += per) {
         const size_t nr = std::min(per, n - r0);
-        cudaStream_t st = npieces > 1 ? s->blk_stream[k & 1] : (cudaStream_t)0;
+        cudaStream_t st = npieces > 1 ? s->blk_stream[k & 3] : (cudaStream_t)0;
         double* din = (double*)s->scratch_in.p + r0 * d;
         double* dout = (double*)s->scratch_out.p + r0;
         if (!cuda_ok(cudaMemcpyAsync(din, theta + r0 * d, nr * d * sizeof(double), cudaMemcpyHostToDevice, st), "H2D theta")) return CARMA_ERR_CUDA;
@@ -852,7 +861,8 @@ int carma_loglik_batch(carma_series_t s, int kind, int p, int q, const carma_pri
         if (!cuda_ok(cudaMemcpyAsync(logpost + r0, dout, nr * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H logpost")) return CARMA_ERR_CUDA;
     }
     if (npieces > 1) {
-        if (!cuda_ok(cudaStreamSynchronize(s->blk_stream[0]), "loglik_batch sync") || !cuda_ok(cudaStreamSynchronize(s->blk_stream[1]), "loglik_batch sync")) return CARMA_ERR_CUDA;
+        for (int k = 0; k < 4; k++)
+            if (!cuda_ok(cudaStreamSynchronize(s->blk_stream[k]), "loglik_batch sync")) return CARMA_ERR_CUDA;
     } else if (!cuda_ok(cudaStreamSynchronize(0), "loglik_batch sync")) {
         return CARMA_ERR_CUDA;
     }

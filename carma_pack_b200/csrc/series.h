@@ -62,7 +62,7 @@ struct carma_series {
     // pipeline slots for the asynchronous host-buffer entry points (own stream + buffers each)
     carma::DevBuf slot_in[CARMA_N_SLOTS], slot_out[CARMA_N_SLOTS];
     cudaStream_t slot_stream[CARMA_N_SLOTS] = {};
-    cudaStream_t blk_stream[2] = {nullptr, nullptr};   // the blocking batch call splits large batches over these
+    cudaStream_t blk_stream[4] = {};   // the blocking batch call splits large batches over these
     carma::SeriesView view() const {
         carma::SeriesView v;
         v.dt = d_pack;

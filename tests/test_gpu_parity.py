@@ -316,6 +316,37 @@ def test_multi_series_ragged(C, O):
     m.close()
 
 
+def test_multi_series_short_curves_at_every_alignment(C, O):
+    """K4 fetches a curve in 32-byte blocks of four steps after peeling a misaligned start: curves of 2..17 points
+    starting at every offset modulo 4 (heads of 0..3 scalar steps, zero or more blocks, tails of 0..3 steps)."""
+    from carma_pack_b200 import synth
+    rng = np.random.default_rng(19)
+    ar, ma, s2 = synth.carma31_truth()
+    lens = [int(n) for n in rng.permutation(np.repeat(np.arange(2, 18), 4))]
+    ts, ys, es, off = [], [], [], [0]
+    for ny in lens:
+        t = synth.cauchy_times(ny, rng)
+        y = 5.0 + synth.carma_process(t, s2, ar, ma, rng) + 0.1 * rng.standard_normal(ny)
+        ts.append(t); ys.append(y); es.append(np.full(ny, 0.1) * rng.uniform(0.5, 2.0, ny)); off.append(off[-1] + ny)
+    assert {o % 4 for o in off[:-1]} == {0, 1, 2, 3}
+    t, y, e = np.concatenate(ts), np.concatenate(ys), np.concatenate(es)
+    th = np.tile(np.array([1.0, 1.0, 5.0, -1.0, -0.5, -3.0, 0.5]), (len(lens), 1))
+    th[:, 2] += 0.05 * rng.standard_normal(len(lens))
+    m = C.MultiSeries(t, y, e, off)
+    got = m.loglik(C.KIND_CARMA, 3, 1, th, flags=C.IGNORE_BOUNDS)
+    opri = [O.default_prior(ts[c], ys[c]) for c in range(len(lens))]
+    want = O.logdensity_multi(O.KIND_CARMA, 3, 1, t, y, e, off, th, opri, ignore_prior=True)
+    assert np.isfinite(want).all()
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    # and the same curves one by one through K1 (series in shared memory): same recursion, different loads
+    for c in (0, 5, 17, 40, len(lens) - 1):
+        s1 = C.Series(ts[c], ys[c], es[c])
+        one = s1.loglik(C.KIND_CARMA, 3, 1, th[c:c + 1], prior=s1.default_prior(), flags=C.IGNORE_BOUNDS)
+        np.testing.assert_allclose(one, got[c:c + 1], rtol=1e-11)
+        s1.close()
+    m.close()
+
+
 def test_philox_bit_exact_and_tdist(C, O):
     rng = np.random.default_rng(1)
     for _ in range(20):
