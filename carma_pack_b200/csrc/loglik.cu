@@ -176,7 +176,7 @@ constexpr int K4_BLOCK = 64;
 // BLK4: the curve is fetched four steps per access with the next block in flight (filter_span_blocks); false: one
 // step per access, one step ahead (CARMA_K4_LOADS=scalar, kept for comparison)
 template <int P, bool GTAB, bool BLK4>
-__global__ void __launch_bounds__(K4_BLOCK)
+__global__ void __launch_bounds__(K4_BLOCK, P <= 3 ? 8 : 1)   // P <= 3: 128 registers, 8 blocks (4 warps per scheduler); measured at P = 3
 multi_loglik_kernel(const double* __restrict__ dt, const double* __restrict__ y, const double* __restrict__ e2,
                     const long long* __restrict__ off, size_t ncurves, double dt_max, int kind, int q, int d, unsigned flags,
                     const carma_prior_t* __restrict__ priors, const double* __restrict__ theta,
