@@ -249,22 +249,37 @@ def test_loglik_stress_all_orders(C, O):
 
 
 def test_async_pipeline_equals_blocking_call(C):
-    """carma_loglik_batch_async/_wait (two slots) returns exactly what the blocking call returns."""
+    """carma_loglik_batch_async/_wait (CARMA_N_SLOTS = 4 slots) returns exactly what the blocking call returns, with
+    two and with four steps in flight; the blocking call itself (four pieces on four streams for >= 16,384 rows)
+    equals one launch over device-resident rows."""
+    import ctypes
+    import torch
     from carma_pack_b200 import synth
     t, y, e = synth.readme_series(270, 3)
     s = C.Series(t, y, e)
     pr = s.default_prior()
-    batches = [np.ascontiguousarray(synth.theta_batch(4096 + 512 * k, t, y, seed=k)) for k in range(5)]
+    batches = [np.ascontiguousarray(synth.theta_batch(4096 + 512 * k, t, y, seed=k)) for k in range(9)]
     want = [s.loglik(C.KIND_CARMA, 5, 3, b, prior=pr) for b in batches]
-    outs = [np.empty(b.shape[0]) for b in batches]
-    for k, b in enumerate(batches):
-        slot = k & 1
-        if k >= 2:
+    for nslot in (2, 4):
+        outs = [np.empty(b.shape[0]) for b in batches]
+        for k, b in enumerate(batches):
+            slot = k % nslot
+            if k >= nslot:
+                s.loglik_wait(slot)
+            s.loglik_async(C.KIND_CARMA, 5, 3, b.ctypes.data, outs[k].ctypes.data, b.shape[0], pr, slot)
+        for slot in range(nslot):
             s.loglik_wait(slot)
-        s.loglik_async(C.KIND_CARMA, 5, 3, b.ctypes.data, outs[k].ctypes.data, b.shape[0], pr, slot)
-    s.loglik_wait(0); s.loglik_wait(1)
-    for k in range(5):
-        assert np.array_equal(outs[k], want[k], equal_nan=True)
+        for k in range(len(batches)):
+            assert np.array_equal(outs[k], want[k], equal_nan=True)
+    with pytest.raises(C.CarmaError):
+        s.loglik_async(C.KIND_CARMA, 5, 3, batches[0].ctypes.data, outs[0].ctypes.data, 16, pr, 4)
+    big = np.ascontiguousarray(synth.theta_batch(40000, t, y, seed=77))
+    got = s.loglik(C.KIND_CARMA, 5, 3, big, prior=pr)              # four pieces
+    d_th = torch.from_numpy(big).cuda()
+    d_out = torch.empty(big.shape[0], dtype=torch.float64, device="cuda")
+    s.loglik_dev(C.KIND_CARMA, 5, 3, d_th.data_ptr(), d_out.data_ptr(), big.shape[0], pr, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(got, d_out.cpu().numpy(), equal_nan=True)
     s.close()
 
 
