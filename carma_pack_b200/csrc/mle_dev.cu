@@ -11,9 +11,8 @@
 //     of latency;
 //   * lane 0 runs the O(m d) optimiser arithmetic (two-loop recursion, Armijo test, curvature test, restarts) on
 //     the warp's shared-memory work area;
-//   * a block is four warps, one per SM sub-partition (blocks of a single warp were all placed on the same
-//     sub-partition: eight concurrent model fits ran no faster than four), sharing one copy of the light curve in
-//     shared memory; after that copy the warps never synchronise again: fits differ tenfold in their iteration
+//   * a block is four warps, one per SM sub-partition, and an SM holds one block; the warps share one copy of the
+//     light curve in shared memory; after that copy the warps never synchronise again: fits differ tenfold in their iteration
 //     counts, so each warp takes its next start from a queue (an atomic counter) when it is done.
 //
 // carma_mle_grid_device fits SEVERAL models in the same launch (choose_order: 28 models x 100 starts): the queue runs
@@ -44,7 +43,12 @@ namespace carma {
 namespace {
 
 constexpr int ML_WARPS = 4;              // one warp per SM sub-partition; a warp owns one start at a time (work queue)
-constexpr int ML_BLOCKS_PER_SM = 3;      // 168 registers x 128 threads x 3
+// ONE block per SM, i.e. one warp per sub-partition: a second or third warp on a scheduler slows this kernel down by
+// more than it adds (28 x 100 starts: 0.67 s with one block per SM, 0.90 with two, 0.75-0.83 with three; 28 x 300
+// starts: 1.02 against 1.39-1.43 s, profiles/r03y_mle_blocks_per_sm.txt) -- the warps of different fits run different
+// orders' loops and prologues through one instruction cache and keep 3 kB of local memory each in one L1 -- and the
+// register allocation is free to use 255 registers.
+constexpr int ML_BLOCKS_PER_SM = 1;
 constexpr int ML_M = 8;                  // history pairs kept per start
 constexpr int ML_D = MAX_D;              // row stride of the work arrays
 constexpr double ML_BIG = 1e300;
