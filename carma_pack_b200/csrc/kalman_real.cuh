@@ -469,6 +469,7 @@ __host__ __device__ __noinline__ double loglik_exact_slow(const RealParams<P>& p
         else y_i = src.get_y(i);
         const double innov = (y_i - prm.mu) - kf.mean;
         ll += -0.5 * log(kf.var) - 0.5 * innov * innov / kf.var;
+        if (ll != ll) return ll;   // NaN stays NaN whatever follows (a negative or NaN variance): no need to finish the series
         if (i + 1 < ny) kf.template advance<false>(prm, tb, innov, 1.0 / kf.var, dt_i, e_i);
     }
     return ll;

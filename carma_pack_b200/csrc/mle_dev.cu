@@ -24,10 +24,12 @@
 //
 // The algorithm is lbfgs_core's, decision for decision (projected L-BFGS, history 8 per start, forward differences
 // with a backward retry at an infeasible point, speculative gradient at the full step, two history-reset restarts,
-// the same stopping rules), and lane 0 does its arithmetic with explicitly rounded multiplies and adds, i.e.
-// without FMA contraction, like the host compiler.  The trial points themselves are evaluated by the
-// register-resident prologue (K1 uses the shared-memory LU variant), so a fit follows the host fit to rounding,
-// not bit for bit; tests compare the optima, not the paths.
+// the same stopping rules), lane 0 does its arithmetic with explicitly rounded multiplies and adds, i.e. without FMA
+// contraction, like the host compiler, and the trial points are evaluated by K1's arithmetic (the prologue with its
+// LU in shared memory, the same filter loop): a fit takes the host fit's path and ends at the same point with the
+// same value after the same number of iterations, bit for bit (tested).  Only the evaluation counts differ: a
+// backtracking round tries every halving of the step that fits into the warp's free lanes, the host loop four per
+// launch; the first candidate that passes is taken either way.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -52,7 +54,8 @@ constexpr int ML_BLOCKS_PER_SM = 1;
 constexpr int ML_M = 8;                  // history pairs kept per start
 constexpr int ML_D = MAX_D;              // row stride of the work arrays
 constexpr double ML_BIG = 1e300;
-constexpr size_t ML_SMEM_MAX = 96 * 1024;
+constexpr size_t ML_SMEM_MAX = 200 * 1024;
+constexpr int ML_LU = 2 * MAX_P * MAX_P * 32;   // LU scratch of the prologue per warp, doubles
 
 struct MleDevParams {     // the optimiser's options, common to all jobs of a launch
     int maxiter, history, max_backtrack;
@@ -84,10 +87,12 @@ __device__ __forceinline__ double min_(double a, double b) { return (b < a) ? b 
 // -LogDensity(theta), non-finite -> BIG (GpuObjective::run of mle.cu)
 template <int P>
 __device__ __noinline__ double neg_logdensity(const MleDevParams& mp, const MleJob& job, const SeriesView& sv, const MathTab& tb,
-                                              const double* th, const double* sdt, const double* sy, const double* se) {
+                                              const double* th, const double* sdt, const double* sy, const double* se,
+                                              double* lu) {
     RealParams<P> prm;
     double lp;
-    if (transform_theta<P>(job.kind, job.q, job.flags, job.prior, th, sv.dt_max, prm) != TT_OK) {
+    // the P x P complex LU of the prologue works in the warp's shared-memory scratch ([element][lane]), as in K1
+    if (transform_theta<P, false, true>(job.kind, job.q, job.flags, job.prior, th, sv.dt_max, prm, nullptr, lu, 32) != TT_OK) {
         lp = -INFINITY;
     } else {
         KalmanReal<P> kf;
@@ -117,6 +122,7 @@ struct WarpFit {
     const double *sdt, *sy, *se;
     const double *lower, *upper;
     int lane, d;
+    double* lu;   // this lane's column of the warp's LU scratch
     // work area
     double *pts, *fv, *x, *g, *xn, *gn, *pg, *qv, *dir, *S, *Y, *rho, *alpha;
     int *blocked, *retry;
@@ -148,7 +154,7 @@ struct WarpFit {
             double th[MAX_D];
 #pragma unroll
             for (int j = 0; j < MAX_D; j++) th[j] = (j < d) ? pts[lane * ML_D + j] : 0.0;
-            v = neg_logdensity<P>(mp, job, sv, tb, th, sdt, sy, se);
+            v = neg_logdensity<P>(mp, job, sv, tb, th, sdt, sy, se, lu);
         }
         __syncwarp();
         fv[lane] = v;
@@ -275,15 +281,18 @@ struct WarpFit {
             if (!active) break;
             double slope = 0.0;
             if (lane == 0) slope = direction(nh, h0);
-            // ---- batched Armijo backtracking: four step sizes per round, the first round also carries the d
-            // difference points around the full step
+            // ---- batched Armijo backtracking: as many step sizes per round as there are lanes, the first round also
+            // carries the d difference points around the full step
             double t = 1.0, fn = f;
             int todo = 1, grad_done = 0, tried = 0;
             if (lane == 0)
                 for (int j = 0; j < d; j++) { xn[j] = x[j]; gn[j] = g[j]; }
             for (int round = 0; tried < mp.max_backtrack && todo; round++) {
-                const int nt = min(4, mp.max_backtrack - tried);
+                // every lane the round leaves free carries a further halving of the step: the candidates are those of
+                // the host loop (which tries four per launch), the first one that passes is taken, so the decision is
+                // the same -- but a search that has to go below t = 1/8 costs one evaluation of latency, not several
                 const bool spec = (round == 0);
+                const int nt = min(32 - (spec ? d : 0), mp.max_backtrack - tried);
                 const int per_row = nt + (spec ? d : 0);
                 if (lane == 0) {
                     double tk = t;
@@ -364,7 +373,7 @@ __device__ __noinline__ void fit_start(const MleDevParams& mp, const MleJob& job
                                        const double* sdt, const double* sy, const double* se, const double* lower,
                                        const double* upper, double* area, int lane, const double* x0, double* x_out,
                                        double* f_out, int* nit_out, unsigned long long* nfev_out) {
-    WarpFit<P> fit{mp, job, sv, tb, sdt, sy, se, lower, upper, lane, job.d};
+    WarpFit<P> fit{mp, job, sv, tb, sdt, sy, se, lower, upper, lane, job.d, area + ML_AREA + lane};
     fit.carve(area);
     fit.nfev = 0;
     const int nit = fit.run(x0, x_out, f_out);
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(ML_WARPS * 32, ML_BLOCKS_PER_SM) lbfgs_kernel(
     // from here on the warps of a block never meet again: each takes the next unfitted start from the queue until
     // none is left
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* area = smem + 3 * (size_t)nyp + (size_t)warp * ML_AREA;
+    double* area = smem + 3 * (size_t)nyp + (size_t)warp * (ML_AREA + ML_LU);
     for (;;) {
         unsigned long long row = 0;
         if (lane == 0) row = atomicAdd(next_row, 1ull);
@@ -429,7 +438,7 @@ cudaError_t lbfgs_attrs() {
 cudaError_t launch_lbfgs(const SeriesView& sv, const MleDevParams& mp, const MleJob* jobs, const double* x0, const double* bounds,
                          double* x_out, double* f_out, int* nit, unsigned long long* nfev, unsigned long long* next_row,
                          cudaStream_t st) {
-    const size_t smem = ((mp.series_in_smem ? 3 * (size_t)sv.nyp : 0) + (size_t)ML_WARPS * ML_AREA) * sizeof(double);
+    const size_t smem = ((mp.series_in_smem ? 3 * (size_t)sv.nyp : 0) + (size_t)ML_WARPS * (ML_AREA + ML_LU)) * sizeof(double);
     const cudaError_t attr_err = lbfgs_attrs();
     if (attr_err != cudaSuccess) return attr_err;
     int nsm = 148, dev = 0;
@@ -532,7 +541,7 @@ extern "C" int carma_mle_grid_device(carma_series_t s, int njobs, const carma_ml
     mp.gtol = o.gtol; mp.ftol = o.ftol; mp.fd_eps = o.fd_eps;
     mp.njobs = njobs;
     mp.total = total;
-    mp.series_in_smem = ((3 * (size_t)sv.nyp + (size_t)ML_WARPS * ML_AREA) * sizeof(double) <= ML_SMEM_MAX) ? 1 : 0;
+    mp.series_in_smem = ((3 * (size_t)sv.nyp + (size_t)ML_WARPS * (ML_AREA + ML_LU)) * sizeof(double) <= ML_SMEM_MAX) ? 1 : 0;
     if (!cuda_ok(launch_lbfgs(sv, mp, d_jobs, din, d_b, dout, d_f, d_nit, d_nfev, d_next, st), "lbfgs_kernel launch")) return CARMA_ERR_CUDA;
     std::vector<double> rx(xdoubles), rf(total);
     std::vector<int> rnit(njobs);

@@ -163,8 +163,9 @@ int carma_mle_batch(carma_series_t s, int kind, int p, int q, const carma_prior_
 /* The same fits with the optimiser itself on the device (one kernel launch per call): a warp owns a start, its lanes
  * evaluate the trial points of a round (the d difference points of a gradient, the step sizes of a backtracking
  * round) concurrently, lane 0 runs the L-BFGS arithmetic.  Same algorithm, options and outputs as carma_mle_batch
- * (history <= 8); an iteration costs one evaluation of latency instead of a launch, two copies and a synchronise, and
- * no start waits for another.  nit_out: the largest iteration count over the starts. */
+ * (history <= 8) -- x_out, f_out and nit_out are bitwise those of carma_mle_batch, nfev_out is larger (more step
+ * sizes tried per round); an iteration costs one evaluation of latency instead of a launch, two copies and a
+ * synchronise, and no start waits for another.  nit_out: the largest iteration count over the starts. */
 int carma_mle_batch_device(carma_series_t s, int kind, int p, int q, const carma_prior_t* prior, unsigned flags,
                            size_t nstart, const double* x0, const double* lower, const double* upper,
                            const carma_mle_opts_t* opts, double* x_out, double* f_out, int* nit_out,

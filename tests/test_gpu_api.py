@@ -277,27 +277,29 @@ def test_native_optimizer_matches_numpy_twin(cm):
 
 def test_device_optimizer_matches_the_host_loop(cm):
     """carma_mle_batch_device (the whole fit of a start inside one kernel, a warp per start) against carma_mle_batch
-    (host loop) from the same starts.  Same algorithm decision for decision; the trial points go through a different
-    build of the prologue, so low orders agree start by start and high orders (forward differences on flat, multi-modal
-    surfaces amplify rounding) agree in the best optimum and for the majority of starts."""
+    (host loop) from the same starts.  Same algorithm decision for decision, the trial points evaluated by the same
+    arithmetic as K1 (shared-memory LU prologue) and lane 0's optimiser arithmetic rounded like the host compiler's:
+    the two take the same path, so every start ends at the same point with the same value after the same number of
+    iterations -- bit for bit.  (The evaluation counts differ: the device tries every halving of a step that fits
+    into the warp's free lanes at once, the host loop four per launch.)"""
     from carma_pack_b200 import synth
     t, y, e = synth.readme_series(200, 11)
     model = cm.CarmaModel(t, y, e)
-    for p, q, frac in ((1, 0, 0.95), (2, 0, 0.95), (3, 1, 0.85), (5, 2, 0.5)):
+    for p, q in ((1, 0), (2, 0), (3, 1), (5, 2), (7, 4)):
         a = model.get_mle(p, q, ntrials=32, seed=21, optimizer="native")
         b = model.get_mle(p, q, ntrials=32, seed=21, optimizer="device")
         assert np.isfinite(a.fun) and np.isfinite(b.fun)
-        assert abs(a.fun - b.fun) < 1e-3 * max(1.0, abs(a.fun)), (p, q, a.fun, b.fun)
         fa, fb = np.asarray(a.all_fun), np.asarray(b.all_fun)
-        both = (fa < 1e299) & (fb < 1e299)
+        np.testing.assert_array_equal(fa, fb)
+        np.testing.assert_array_equal(np.asarray(a.all_x), np.asarray(b.all_x))
+        assert a.nit == b.nit and a.fun == b.fun
+        both = fb < 1e299
         assert both.sum() >= 24
-        close = np.abs(fa[both] - fb[both]) < 1e-4 * np.maximum(1.0, np.abs(fa[both]))
-        assert close.mean() >= frac, (p, q, close.mean())
-        # every device optimum is a genuine function value at a point inside the box
+        # every optimum is a genuine function value at a point inside the box
         kind = cm.KIND_CAR1 if p == 1 else (cm.KIND_CARMA if q > 0 else cm.KIND_CARP)
         flags = 0 if p == 1 else cm.IGNORE_BOUNDS
         re = -model.series.loglik(kind, p, q, b.all_x[both], prior=model.series.default_prior(True), flags=flags)
-        np.testing.assert_allclose(re, fb[both], rtol=1e-9)
+        np.testing.assert_array_equal(re, fb[both])
         assert b.nfev > 0 and b.nit >= 1
     # a start's fit does not depend on the other starts of the launch
     kind, x0, lo, hi, prior, flags = model.mle_starts(3, 1, 16, seed=5)
