@@ -226,9 +226,12 @@ cudaError_t launch_multi_loglik(const carma_multi_series* m, int kind, int p, in
 #define LAUNCH_K4_AS(PP, GT, B4)                                                                                      \
     multi_loglik_kernel<PP, GT, B4><<<grid, K4_BLOCK, 0, stream>>>(m->d_dt, m->d_y, m->d_e2, m->d_off, m->ncurves,    \
                                                                    m->dt_max, kind, q, d, flags, d_priors, d_theta, d_out)
+    // the block loads need the three arrays to sit alike within a 32-byte sector (separate allocations: they do)
+    const bool alike = ((((size_t)m->d_dt ^ (size_t)m->d_y) | ((size_t)m->d_dt ^ (size_t)m->d_e2)) & 31u) == 0;
+    const bool scalar_now = scalar_loads || !alike;
 #define LAUNCH_K4(PP)                                                                                                 \
-    if (smem_tab) { if (scalar_loads) LAUNCH_K4_AS(PP, false, false); else LAUNCH_K4_AS(PP, false, true); }           \
-    else { if (scalar_loads) LAUNCH_K4_AS(PP, true, false); else LAUNCH_K4_AS(PP, true, true); }
+    if (smem_tab) { if (scalar_now) LAUNCH_K4_AS(PP, false, false); else LAUNCH_K4_AS(PP, false, true); }             \
+    else { if (scalar_now) LAUNCH_K4_AS(PP, true, false); else LAUNCH_K4_AS(PP, true, true); }
     switch (p) {
         case 1: LAUNCH_K4(1); break;
         case 2: LAUNCH_K4(2); break;
