@@ -326,6 +326,19 @@ def test_device_optimizer_matches_the_host_loop(cm):
     assert model.series.mle_grid([]) == []
 
 
+def test_device_optimizer_on_a_series_too_long_for_shared_memory(cm):
+    """ny = 3000: the series plus the warps' work areas exceed the kernel's shared memory, the trial points are
+    evaluated from global memory -- still the host loop's fits bit for bit."""
+    from carma_pack_b200 import synth
+    t, y, e = synth.readme_series(3000, 5)
+    model = cm.CarmaModel(t, y, e)
+    a = model.get_mle(3, 1, ntrials=8, seed=3, optimizer="native")
+    b = model.get_mle(3, 1, ntrials=8, seed=3, optimizer="device")
+    assert np.isfinite(b.fun) and a.nit == b.nit
+    np.testing.assert_array_equal(np.asarray(a.all_fun), np.asarray(b.all_fun))
+    np.testing.assert_array_equal(np.asarray(a.all_x), np.asarray(b.all_x))
+
+
 def test_fast_filter_and_predict_equal_the_general_complex_kernels(cm):
     """KalmanFilterp::Filter / Predict for conjugate-symmetric roots run in the real-half recursion (time-parallel
     forward filter + per-query coefficient pass resuming from stored states); the general complex kernels
